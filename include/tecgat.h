@@ -1,0 +1,138 @@
+/* tecgat.h -- C ABI of libtecgat.so: the B200 (sm_100a) GATv2 SpatialEncoder + haversine graph path.
+ *
+ * The reference (PANXIONG-CN/TEC-MoLLM) is pure Python and has NO native ABI for this path; each
+ * entry point below replaces one step that the reference reaches through torch_geometric / ATen /
+ * scikit-learn / scipy, cited as reference file:line (paths relative to /root/reference) or as the
+ * step of PyG's GATv2Conv.forward.
+ *
+ * Conventions
+ *   - plain C types only; every pointer named *_dev is a device pointer, *_host a host pointer;
+ *   - all device work is enqueued on `stream` (a cudaStream_t passed as void*); no hidden syncs
+ *     except where stated (plan creation, graph builder: one-time set-up calls);
+ *   - the caller owns every buffer (PyTorch tensors on the Python side); the only library-owned
+ *     object is the immutable graph plan;
+ *   - every function returns 0 on success, a negative TECGAT_E* code otherwise, and never throws or
+ *     exits; tecgat_last_error() returns a thread-local message for the last failure;
+ *   - deterministic: no floating-point atomics anywhere.
+ *
+ * Row-major layouts, R = S*N rows (snapshot-major: row = s*N + node):
+ *   x  (R, F)   fp32        xl, xr (R, H*C) storage dtype (fp32, or bf16 for the autocast contract)
+ *   y  (R, H*C) fp32        m, den (R, H)   fp32  (softmax shift and denominator, saved for backward)
+ */
+#ifndef TECGAT_H_
+#define TECGAT_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TECGAT_ABI_VERSION 1
+
+/* error codes */
+#define TECGAT_OK 0
+#define TECGAT_EINVAL (-1)  /* bad argument (shape, dtype, null pointer, unsupported size) */
+#define TECGAT_ECUDA (-2)   /* CUDA runtime error (message carries cudaGetErrorString) */
+#define TECGAT_ENOMEM (-3)  /* host allocation failure */
+#define TECGAT_ENOSUP (-4)  /* configuration not supported by the compiled kernels */
+
+/* storage dtype of xl / xr / dxl / dxr */
+#define TECGAT_F32 0
+#define TECGAT_BF16 1
+
+/* snapshot modes */
+#define TECGAT_MODE_SHARED 0  /* the N-node graph applies to every snapshot (intended semantics)   */
+#define TECGAT_MODE_LITERAL 1 /* modules.py:353-356 exactly as written: only snapshot 0 sees edges */
+
+/* projection implementations */
+#define TECGAT_PROJ_TC 0   /* tcgen05 tensor-core GEMM fed by bulk-TMA (product path)               */
+#define TECGAT_PROJ_FFMA 1 /* CUDA-core kernel; used to cross-check the tensor-core path in tests   */
+
+typedef struct tecgat_plan tecgat_plan_t;
+
+int tecgat_abi_version(void);
+const char *tecgat_last_error(void);
+
+/* ---- graph plan: replaces remove_self_loops + add_self_loops done on EVERY forward by PyG
+ *      (GATv2Conv.forward, called at src/model/modules.py:356) with a one-time,
+ *      cached, destination-sorted CSR (+ source-sorted CSR for the atomic-free backward and a
+ *      per-tile source-row window).  Synchronises `stream` once (edge list is read back to host). */
+int tecgat_plan_create(const int64_t *edge_index_dev, int64_t num_edges, int32_t num_nodes,
+                       int32_t tile_nodes, void *stream, tecgat_plan_t **plan_out);
+int tecgat_plan_destroy(tecgat_plan_t *plan);
+/* info[0]=E (kept edges + N self loops) [1]=max in-degree [2]=max out-degree [3]=tiles
+ * [4]=tile_nodes [5]=max source-window rows [6]=num_nodes [7]=kept (non-self) edges */
+int tecgat_plan_info(const tecgat_plan_t *plan, int64_t *info8_host);
+/* Host copies for tests: rowptr (N+1), col (E) = source node of CSR slot k, eid (E) = index of that
+ * edge in PyG's post-surgery edge order (kept edges in input order, then self loops). */
+int tecgat_plan_export(const tecgat_plan_t *plan, int32_t *rowptr_host, int32_t *col_host,
+                       int32_t *eid_host);
+
+/* ---- projections: replace lin_l / lin_r (two torch.nn.functional.linear -> cuBLAS addmm, SURVEY.md
+ *      K1) and their autograd backward (K10).  [xl|xr] = x [Wl;Wr]^T + [bl|br] in ONE pass over x. */
+int tecgat_project_fwd(const float *x_dev, const float *wl_dev, const float *bl_dev,
+                       const float *wr_dev, const float *br_dev, void *xl_dev, void *xr_dev,
+                       int64_t rows, int32_t in_channels, int32_t hc, int32_t dtype, int32_t impl,
+                       void *stream);
+/* workspace bytes needed by tecgat_project_bwd */
+int64_t tecgat_project_bwd_workspace(int64_t rows, int32_t in_channels, int32_t hc, int32_t impl);
+/* dx = dxl Wl + dxr Wr (skipped when dx_dev is NULL); dWl = dxl^T x; dbl = sum dxl; same for r.   */
+int tecgat_project_bwd(const void *dxl_dev, const void *dxr_dev, const float *x_dev,
+                       const float *wl_dev, const float *wr_dev, float *dx_dev, float *dwl_dev,
+                       float *dbl_dev, float *dwr_dev, float *dbr_dev, void *workspace_dev,
+                       int64_t rows, int32_t in_channels, int32_t hc, int32_t dtype, int32_t impl,
+                       void *stream);
+
+/* ---- fused edge phase: replaces gather + LeakyReLU*att + segment softmax + dropout + scatter-add
+ *      + bias (~20 ATen launches in PyG) with one kernel over all snapshots.
+ *      dropout_p == 0 disables dropout; otherwise keep-mask bit for (snapshot s, CSR slot k, head h)
+ *      is tecgat_dropout_keep(seed, s*E + k, h, p) (see tecgat_dropout_mask_host).                */
+int tecgat_edge_fwd(const tecgat_plan_t *plan, const void *xl_dev, const void *xr_dev,
+                    const float *att_dev, const float *bias_dev, float *y_dev, float *m_dev,
+                    float *den_dev, int32_t snapshots, int32_t heads, int32_t out_channels,
+                    float negative_slope, float dropout_p, uint64_t seed, int32_t mode,
+                    int32_t dtype, void *stream);
+int64_t tecgat_edge_bwd_workspace(const tecgat_plan_t *plan, int32_t snapshots, int32_t heads,
+                                  int32_t out_channels);
+/* backward of the edge phase, atomic-free: every node's lane reduces its incoming edges (d xr) and its
+ * outgoing edges (d xl) from the two CSR orientations; d att / d bias via deterministic two-stage sums. */
+int tecgat_edge_bwd(const tecgat_plan_t *plan, const void *xl_dev, const void *xr_dev,
+                    const float *att_dev, const float *bias_dev, const float *y_dev,
+                    const float *m_dev, const float *den_dev, const float *gy_dev, void *dxl_dev,
+                    void *dxr_dev, float *datt_dev, float *dbias_dev, void *workspace_dev,
+                    int32_t snapshots, int32_t heads, int32_t out_channels, float negative_slope,
+                    float dropout_p, uint64_t seed, int32_t mode, int32_t dtype, void *stream);
+
+/* Host restatement of the kernels' counter-based dropout RNG (pure integer arithmetic), so tests can
+ * hand the oracle exactly the mask the kernels used.  keep_host: (count, heads) bytes, slot-major.  */
+int tecgat_dropout_mask_host(uint64_t seed, int64_t first_slot, int64_t count, int32_t heads,
+                             float dropout_p, uint8_t *keep_host);
+
+/* ---- graph builder: replaces calculate_haversine_distance_matrix (src/graph/graph_constructor.py:34-59,
+ *      sklearn haversine_distances in fp64), construct_binary_adjacency (:61-81, inclusive `<=`, zero
+ *      diagonal), symmetrically_normalize_adjacency (:99-128) and the COO extraction of
+ *      convert_to_pyg_and_save (:141-144).  Inputs are per-node coordinates in RADIANS (device, fp64).
+ *
+ *  tecgraph_distance_rows : dense rows D[r0:r1, 0:n] in km (fp64), for the dense-API mirror.
+ *  tecgraph_edges_count   : pass 1 -- per-row neighbour counts (deg_dev, int32, n entries), total in
+ *                           *total_host; pairs whose distance is within a relative guard band of the
+ *                           threshold are re-evaluated on the host with the reference's exact libm
+ *                           formula so the edge SET is bit-exact (synchronises the stream).
+ *  tecgraph_edges_fill    : pass 2 -- edge_index (2, E) int64 row-major (row ascending, column ascending
+ *                           inside a row, exactly scipy's COO order) and edge_weight fp32 =
+ *                           fp32((1/sqrt(deg_r) * 1.0) * 1/sqrt(deg_c)).                              */
+typedef struct tecgraph_ctx tecgraph_ctx_t;
+int tecgraph_distance_rows(const double *lat_dev, const double *lon_dev, int64_t n, int64_t r0,
+                           int64_t r1, double radius_km, double *out_dev, void *stream);
+int tecgraph_edges_count(const double *lat_dev, const double *lon_dev, int64_t n, double thr_km,
+                         double radius_km, void *stream, tecgraph_ctx_t **ctx_out,
+                         int64_t *total_host, int64_t *ambiguous_host);
+int tecgraph_edges_fill(tecgraph_ctx_t *ctx, int64_t *edge_index_dev, float *edge_weight_dev,
+                        void *stream);
+int tecgraph_ctx_destroy(tecgraph_ctx_t *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TECGAT_H_ */

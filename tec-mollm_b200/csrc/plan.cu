@@ -1,0 +1,222 @@
+// plan.cu -- one-time graph plan: what PyG redoes on every forward (remove_self_loops + add_self_loops,
+// boolean-mask nonzero with a device->host sync; GATv2Conv.forward called at
+// /root/reference/src/model/modules.py:356) becomes a cached, immutable structure:
+//   * destination-sorted CSR (stable: a destination's in-edges keep the input order, self loop last,
+//     i.e. exactly PyG's per-destination accumulation order on CPU),
+//   * source-sorted CSR with, per out-slot, the in-CSR slot of the same edge (dropout counter),
+//   * per tile of `tile_nodes` consecutive nodes, the window [lo, hi) of rows the tile touches either as
+//     in-neighbours or out-neighbours -- the contiguous slab the edge kernels stage in shared memory.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+static thread_local std::string g_last_error;
+
+void tecgat_set_error(const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+}
+
+extern "C" const char *tecgat_last_error(void) { return g_last_error.c_str(); }
+extern "C" int tecgat_abi_version(void) { return TECGAT_ABI_VERSION; }
+
+template <typename T>
+static int upload(T **dst, const std::vector<T> &src, cudaStream_t st) {
+    const size_t bytes = std::max<size_t>(src.size(), 1) * sizeof(T);
+    TG_CUDA(cudaMalloc(reinterpret_cast<void **>(dst), bytes));
+    if (!src.empty()) TG_CUDA(cudaMemcpyAsync(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+    return TECGAT_OK;
+}
+
+extern "C" int tecgat_plan_destroy(tecgat_plan_t *p) {
+    if (!p) return TECGAT_OK;
+    cudaFree(p->rowptr_in);
+    cudaFree(p->col_in);
+    cudaFree(p->rowptr_out);
+    cudaFree(p->col_out);
+    cudaFree(p->slot_out);
+    cudaFree(p->tile_lo);
+    cudaFree(p->tile_hi);
+    free(p->h_rowptr_in);
+    free(p->h_col_in);
+    free(p->h_eid_in);
+    delete p;
+    return TECGAT_OK;
+}
+
+extern "C" int tecgat_plan_create(const int64_t *edge_index_dev, int64_t num_edges, int32_t num_nodes,
+                                  int32_t tile_nodes, void *stream, tecgat_plan_t **plan_out) {
+    TG_REQUIRE(plan_out != nullptr, TECGAT_EINVAL, "plan_create: plan_out is NULL");
+    *plan_out = nullptr;
+    TG_REQUIRE(num_nodes > 0, TECGAT_EINVAL, "plan_create: num_nodes must be positive (got %d)", num_nodes);
+    TG_REQUIRE(num_edges >= 0, TECGAT_EINVAL, "plan_create: negative edge count");
+    TG_REQUIRE(num_edges == 0 || edge_index_dev != nullptr, TECGAT_EINVAL, "plan_create: edge_index is NULL");
+    TG_REQUIRE(tile_nodes >= 8 && tile_nodes <= 1024, TECGAT_EINVAL, "plan_create: tile_nodes %d outside [8, 1024]",
+               tile_nodes);
+    TG_REQUIRE(num_edges + num_nodes < (int64_t(1) << 31), TECGAT_ENOSUP, "plan_create: more than 2^31 edges");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t N = num_nodes, E0 = num_edges;
+
+    std::vector<int64_t> ei(static_cast<size_t>(2 * E0));
+    if (E0 > 0) {
+        TG_CUDA(cudaMemcpyAsync(ei.data(), edge_index_dev, sizeof(int64_t) * 2 * E0, cudaMemcpyDeviceToHost, st));
+        TG_CUDA(cudaStreamSynchronize(st));
+    }
+    const int64_t *src = ei.data(), *dst = ei.data() + E0;
+    int64_t kept = 0;
+    for (int64_t e = 0; e < E0; ++e) {
+        if (src[e] < 0 || src[e] >= N || dst[e] < 0 || dst[e] >= N) {
+            tecgat_set_error("plan_create: edge %lld = (%lld -> %lld) outside [0, %d)", (long long)e, (long long)src[e],
+                             (long long)dst[e], num_nodes);
+            return TECGAT_EINVAL;
+        }
+        kept += (src[e] != dst[e]);
+    }
+    const int64_t E = kept + N;
+
+    tecgat_plan_t *p = new (std::nothrow) tecgat_plan_t();
+    TG_REQUIRE(p != nullptr, TECGAT_ENOMEM, "plan_create: out of host memory");
+    cudaGetDevice(&p->device);
+    p->num_nodes = num_nodes;
+    p->tile_nodes = tile_nodes;
+    p->num_tiles = static_cast<int32_t>((N + tile_nodes - 1) / tile_nodes);
+    p->num_edges = E;
+    p->kept_edges = kept;
+
+    // ---- destination-sorted CSR (stable counting sort; self loop appended last per row) ----------
+    std::vector<int32_t> rp_in(N + 1, 0), rp_out(N + 1, 0);
+    for (int64_t e = 0; e < E0; ++e)
+        if (src[e] != dst[e]) {
+            rp_in[dst[e] + 1]++;
+            rp_out[src[e] + 1]++;
+        }
+    for (int64_t i = 0; i < N; ++i) {
+        rp_in[i + 1] += 1;   // self loop
+        rp_out[i + 1] += 1;
+    }
+    for (int64_t i = 0; i < N; ++i) {
+        p->max_in_deg = std::max(p->max_in_deg, rp_in[i + 1]);
+        p->max_out_deg = std::max(p->max_out_deg, rp_out[i + 1]);
+        rp_in[i + 1] += rp_in[i];
+        rp_out[i + 1] += rp_out[i];
+    }
+    std::vector<int32_t> col_in(E), eid_in(E), col_out(E), slot_out(E);
+    {
+        std::vector<int32_t> cur_in(rp_in.begin(), rp_in.end() - 1), cur_out(rp_out.begin(), rp_out.end() - 1);
+        std::vector<int32_t> slot_of_edge(E);  // PyG edge id -> in-CSR slot
+        int32_t id = 0;
+        for (int64_t e = 0; e < E0; ++e)
+            if (src[e] != dst[e]) {
+                const int32_t k = cur_in[dst[e]]++;
+                col_in[k] = static_cast<int32_t>(src[e]);
+                eid_in[k] = id;
+                slot_of_edge[id] = k;
+                ++id;
+            }
+        for (int64_t i = 0; i < N; ++i) {
+            const int32_t k = cur_in[i]++;
+            col_in[k] = static_cast<int32_t>(i);
+            eid_in[k] = static_cast<int32_t>(kept + i);
+            slot_of_edge[kept + i] = k;
+        }
+        id = 0;
+        for (int64_t e = 0; e < E0; ++e)
+            if (src[e] != dst[e]) {
+                const int32_t k2 = cur_out[src[e]]++;
+                col_out[k2] = static_cast<int32_t>(dst[e]);
+                slot_out[k2] = slot_of_edge[id];
+                ++id;
+            }
+        for (int64_t i = 0; i < N; ++i) {
+            const int32_t k2 = cur_out[i]++;
+            col_out[k2] = static_cast<int32_t>(i);
+            slot_out[k2] = slot_of_edge[kept + i];
+        }
+    }
+    // ---- per-tile row windows ------------------------------------------------------------------------
+    std::vector<int32_t> lo(p->num_tiles), hi(p->num_tiles);
+    for (int32_t t = 0; t < p->num_tiles; ++t) {
+        const int64_t n0 = int64_t(t) * tile_nodes, n1 = std::min<int64_t>(N, n0 + tile_nodes);
+        int32_t l = static_cast<int32_t>(n0), h = static_cast<int32_t>(n1 - 1);
+        for (int32_t k = rp_in[n0]; k < rp_in[n1]; ++k) {
+            l = std::min(l, col_in[k]);
+            h = std::max(h, col_in[k]);
+        }
+        for (int32_t k = rp_out[n0]; k < rp_out[n1]; ++k) {
+            l = std::min(l, col_out[k]);
+            h = std::max(h, col_out[k]);
+        }
+        lo[t] = l;
+        hi[t] = h + 1;
+        p->max_window = std::max(p->max_window, h + 1 - l);
+    }
+
+    int rc = TECGAT_OK;
+    if ((rc = upload(&p->rowptr_in, rp_in, st)) || (rc = upload(&p->col_in, col_in, st)) ||
+        (rc = upload(&p->rowptr_out, rp_out, st)) || (rc = upload(&p->col_out, col_out, st)) ||
+        (rc = upload(&p->slot_out, slot_out, st)) || (rc = upload(&p->tile_lo, lo, st)) ||
+        (rc = upload(&p->tile_hi, hi, st))) {
+        tecgat_plan_destroy(p);
+        return rc;
+    }
+    p->h_rowptr_in = static_cast<int32_t *>(malloc(sizeof(int32_t) * (N + 1)));
+    p->h_col_in = static_cast<int32_t *>(malloc(sizeof(int32_t) * std::max<int64_t>(E, 1)));
+    p->h_eid_in = static_cast<int32_t *>(malloc(sizeof(int32_t) * std::max<int64_t>(E, 1)));
+    if (!p->h_rowptr_in || !p->h_col_in || !p->h_eid_in) {
+        tecgat_plan_destroy(p);
+        tecgat_set_error("plan_create: out of host memory");
+        return TECGAT_ENOMEM;
+    }
+    memcpy(p->h_rowptr_in, rp_in.data(), sizeof(int32_t) * (N + 1));
+    memcpy(p->h_col_in, col_in.data(), sizeof(int32_t) * E);
+    memcpy(p->h_eid_in, eid_in.data(), sizeof(int32_t) * E);
+    // the uploads read from the std::vectors above: finish them before the vectors go away
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+        tecgat_plan_destroy(p);
+        tecgat_set_error("plan_create: upload failed: %s", cudaGetErrorString(e));
+        return TECGAT_ECUDA;
+    }
+    *plan_out = p;
+    return TECGAT_OK;
+}
+
+extern "C" int tecgat_plan_info(const tecgat_plan_t *p, int64_t *info) {
+    TG_REQUIRE(p && info, TECGAT_EINVAL, "plan_info: NULL argument");
+    info[0] = p->num_edges;
+    info[1] = p->max_in_deg;
+    info[2] = p->max_out_deg;
+    info[3] = p->num_tiles;
+    info[4] = p->tile_nodes;
+    info[5] = p->max_window;
+    info[6] = p->num_nodes;
+    info[7] = p->kept_edges;
+    return TECGAT_OK;
+}
+
+extern "C" int tecgat_plan_export(const tecgat_plan_t *p, int32_t *rowptr, int32_t *col, int32_t *eid) {
+    TG_REQUIRE(p, TECGAT_EINVAL, "plan_export: NULL plan");
+    if (rowptr) memcpy(rowptr, p->h_rowptr_in, sizeof(int32_t) * (p->num_nodes + 1));
+    if (col) memcpy(col, p->h_col_in, sizeof(int32_t) * p->num_edges);
+    if (eid) memcpy(eid, p->h_eid_in, sizeof(int32_t) * p->num_edges);
+    return TECGAT_OK;
+}
+
+extern "C" int tecgat_dropout_mask_host(uint64_t seed, int64_t first_slot, int64_t count, int32_t heads,
+                                        float dropout_p, uint8_t *keep) {
+    TG_REQUIRE(keep && heads > 0 && count >= 0, TECGAT_EINVAL, "dropout_mask_host: bad argument");
+    const uint32_t thr = tg::dropout_threshold(dropout_p);
+    for (int64_t i = 0; i < count; ++i)
+        for (int32_t h = 0; h < heads; ++h)
+            keep[i * heads + h] = tg::dropout_bits(seed, uint64_t(first_slot + i), uint32_t(h), uint32_t(heads)) >= thr;
+    return TECGAT_OK;
+}

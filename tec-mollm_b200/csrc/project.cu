@@ -1,0 +1,34 @@
+// project.cu -- C ABI of the lin_l / lin_r projections: argument checks + implementation choice.
+#include "project.cuh"
+
+extern "C" int tecgat_project_fwd(const float *x, const float *wl, const float *bl, const float *wr, const float *br,
+                                  void *xl, void *xr, int64_t rows, int32_t F, int32_t hc, int32_t dtype, int32_t impl,
+                                  void *stream) {
+    TG_REQUIRE(x && wl && bl && wr && br && xl && xr, TECGAT_EINVAL, "project_fwd: NULL argument");
+    TG_REQUIRE(rows > 0 && F > 0 && hc > 0, TECGAT_EINVAL, "project_fwd: non-positive size");
+    TG_REQUIRE(dtype == TECGAT_F32 || dtype == TECGAT_BF16, TECGAT_EINVAL, "project_fwd: bad dtype %d", dtype);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (impl == TECGAT_PROJ_FFMA) return tg::project_fwd_ffma(x, wl, bl, wr, br, xl, xr, rows, F, hc, dtype, st);
+    TG_REQUIRE(impl == TECGAT_PROJ_TC, TECGAT_EINVAL, "project_fwd: bad impl %d", impl);
+    TG_REQUIRE(tg::project_tc_supported(F, hc), TECGAT_ENOSUP, "project_fwd(tc): in_channels=%d, heads*out_channels=%d outside the tensor-core kernel's range", F, hc);
+    return tg::project_fwd_tc(x, wl, bl, wr, br, xl, xr, rows, F, hc, dtype, st);
+}
+
+extern "C" int64_t tecgat_project_bwd_workspace(int64_t rows, int32_t F, int32_t hc, int32_t impl) {
+    if (rows <= 0 || F <= 0 || hc <= 0) return 0;
+    return impl == TECGAT_PROJ_FFMA ? tg::project_bwd_ffma_workspace(rows, F, hc) : tg::project_bwd_tc_workspace(rows, F, hc);
+}
+
+extern "C" int tecgat_project_bwd(const void *dxl, const void *dxr, const float *x, const float *wl, const float *wr,
+                                  float *dx, float *dwl, float *dbl, float *dwr, float *dbr, void *workspace, int64_t rows,
+                                  int32_t F, int32_t hc, int32_t dtype, int32_t impl, void *stream) {
+    TG_REQUIRE(dxl && dxr && x && wl && wr && dwl && dbl && dwr && dbr && workspace, TECGAT_EINVAL, "project_bwd: NULL argument");
+    TG_REQUIRE(rows > 0 && F > 0 && hc > 0, TECGAT_EINVAL, "project_bwd: non-positive size");
+    TG_REQUIRE(dtype == TECGAT_F32 || dtype == TECGAT_BF16, TECGAT_EINVAL, "project_bwd: bad dtype %d", dtype);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (impl == TECGAT_PROJ_FFMA)
+        return tg::project_bwd_ffma(dxl, dxr, x, wl, wr, dx, dwl, dbl, dwr, dbr, workspace, rows, F, hc, dtype, st);
+    TG_REQUIRE(impl == TECGAT_PROJ_TC, TECGAT_EINVAL, "project_bwd: bad impl %d", impl);
+    TG_REQUIRE(tg::project_tc_supported(F, hc), TECGAT_ENOSUP, "project_bwd(tc): in_channels=%d, heads*out_channels=%d outside the tensor-core kernel's range", F, hc);
+    return tg::project_bwd_tc(dxl, dxr, x, wl, wr, dx, dwl, dbl, dwr, dbr, workspace, rows, F, hc, dtype, st);
+}

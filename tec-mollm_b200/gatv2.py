@@ -1,0 +1,281 @@
+"""Drop-in ``GATv2Conv`` for the TEC-MoLLM SpatialEncoder, backed by ``libtecgat.so`` (sm_100a).
+
+Mirrors the operator the reference instantiates at ``src/model/modules.py:329-336``
+(``torch_geometric.nn.GATv2Conv(in, out, heads=, dropout=, concat=True, add_self_loops=True)``)
+and calls at ``:356`` (``forward(x2d, edge_index)``): same constructor, same parameter names and
+shapes (``lin_l.weight``, ``lin_l.bias``, ``lin_r.weight``, ``lin_r.bias``, ``att``, ``bias`` -- so
+reference checkpoints load with ``strict=True``), same init distributions, same math.
+
+All compute runs in hand-written CUDA through the C ABI (``include/tecgat.h``); this file only
+owns tensors, the cached graph plan and the autograd wiring.  No Triton, no dispatch, no CPU path:
+a non-CUDA input raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from typing import Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import _lib
+
+__all__ = ["GATv2Conv", "GraphPlan", "tile_nodes_for"]
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream(device: torch.device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def tile_nodes_for(heads: int) -> int:
+    """Destination nodes per CTA: one lane per (node, head), at most 256 lanes."""
+    if heads < 1 or heads > 32:
+        raise ValueError(f"heads={heads} unsupported (1..32)")
+    t = 256 // heads
+    return max(8, min(128, (t // 8) * 8))
+
+
+def _proj_impl() -> int:
+    """Tensor-core projections are the product path; ``TECGAT_PROJ=ffma`` selects the CUDA-core
+    cross-check kernels (tests only)."""
+    return _lib.PROJ_FFMA if os.environ.get("TECGAT_PROJ", "tc").lower() == "ffma" else _lib.PROJ_TC
+
+
+class GraphPlan:
+    """Immutable device-side plan of one ``edge_index`` (see csrc/plan.cu).  Replaces the per-forward
+    ``remove_self_loops``/``add_self_loops`` of PyG with a one-time build."""
+
+    def __init__(self, edge_index: torch.Tensor, num_nodes: int, tile_nodes: int):
+        if not edge_index.is_cuda:
+            raise RuntimeError("tec_mollm_b200: edge_index must be a CUDA tensor (no CPU path)")
+        if edge_index.dim() != 2 or edge_index.size(0) != 2 or edge_index.dtype != torch.int64:
+            raise ValueError(f"edge_index must be int64 of shape (2, E); got {edge_index.dtype} {tuple(edge_index.shape)}")
+        ei = edge_index.contiguous()
+        self.device = ei.device
+        self.num_nodes = int(num_nodes)
+        self.tile_nodes = int(tile_nodes)
+        handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.call("tecgat_plan_create", _ptr(ei), ei.size(1), self.num_nodes, self.tile_nodes,
+                      _stream(self.device), C.byref(handle))
+        self._h = handle
+        info = (C.c_int64 * 8)()
+        _lib.call("tecgat_plan_info", self._h, info)
+        (self.num_edges, self.max_in_degree, self.max_out_degree, self.num_tiles, _, self.max_window, _,
+         self.kept_edges) = [int(v) for v in info]
+
+    @property
+    def handle(self):
+        return self._h
+
+    def export(self):
+        """Host copies (numpy int32): rowptr (N+1), col (E), eid (E) -- see tecgat_plan_export."""
+        import numpy as np
+
+        rowptr = np.empty(self.num_nodes + 1, dtype=np.int32)
+        col = np.empty(self.num_edges, dtype=np.int32)
+        eid = np.empty(self.num_edges, dtype=np.int32)
+        _lib.call("tecgat_plan_export", self._h, C.c_void_p(rowptr.ctypes.data), C.c_void_p(col.ctypes.data),
+                  C.c_void_p(eid.ctypes.data))
+        return rowptr, col, eid
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                _lib.lib().tecgat_plan_destroy(h)
+            except Exception:
+                pass
+
+
+class _GATv2Function(torch.autograd.Function):
+    """forward = project_fwd + edge_fwd; backward = edge_bwd + project_bwd (four launches + two tiny
+    fixed-order reductions).  Saved for backward: x, xl, xr, y, m, den (PyG saves 4-6 (S*E, H, C) tensors)."""
+
+    @staticmethod
+    def forward(ctx, x2d, wl, bl, wr, br, att, bias, plan: GraphPlan, S, H, Cc, slope, p, seed, mode, dtype, impl):
+        dev = x2d.device
+        R, F = x2d.shape
+        HC = H * Cc
+        st_dtype = torch.float32 if dtype == _lib.F32 else torch.bfloat16
+        with torch.cuda.device(dev):
+            stream = _stream(dev)
+            xl = torch.empty((R, HC), device=dev, dtype=st_dtype)
+            xr = torch.empty((R, HC), device=dev, dtype=st_dtype)
+            _lib.call("tecgat_project_fwd", _ptr(x2d), _ptr(wl), _ptr(bl), _ptr(wr), _ptr(br), _ptr(xl), _ptr(xr),
+                      R, F, HC, dtype, impl, stream)
+            y = torch.empty((R, HC), device=dev, dtype=torch.float32)
+            m = torch.empty((R, H), device=dev, dtype=torch.float32)
+            den = torch.empty((R, H), device=dev, dtype=torch.float32)
+            _lib.call("tecgat_edge_fwd", plan.handle, _ptr(xl), _ptr(xr), _ptr(att), _ptr(bias), _ptr(y), _ptr(m),
+                      _ptr(den), S, H, Cc, slope, p, seed, mode, dtype, stream)
+        ctx.save_for_backward(x2d, wl, wr, att, bias, xl, xr, y, m, den)
+        ctx.plan = plan
+        ctx.cfg = (S, H, Cc, slope, p, seed, mode, dtype, impl)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x2d, wl, wr, att, bias, xl, xr, y, m, den = ctx.saved_tensors
+        S, H, Cc, slope, p, seed, mode, dtype, impl = ctx.cfg
+        plan: GraphPlan = ctx.plan
+        dev = x2d.device
+        R, F = x2d.shape
+        HC = H * Cc
+        gy = gy.contiguous()
+        if gy.dtype != torch.float32:
+            gy = gy.float()
+        with torch.cuda.device(dev):  # autograd worker threads do not inherit the current device
+            stream = _stream(dev)
+            dxl = torch.empty_like(xl)
+            dxr = torch.empty_like(xr)
+            datt = torch.empty((1, H, Cc), device=dev, dtype=torch.float32)
+            dbias = torch.empty((HC,), device=dev, dtype=torch.float32)
+            ws1 = torch.empty((max(1, _lib.lib().tecgat_edge_bwd_workspace(plan.handle, S, H, Cc)),), device=dev,
+                              dtype=torch.uint8)
+            _lib.call("tecgat_edge_bwd", plan.handle, _ptr(xl), _ptr(xr), _ptr(att), _ptr(bias), _ptr(y), _ptr(m),
+                      _ptr(den), _ptr(gy), _ptr(dxl), _ptr(dxr), _ptr(datt), _ptr(dbias), _ptr(ws1), S, H, Cc, slope, p,
+                      seed, mode, dtype, stream)
+            dx = torch.empty_like(x2d) if ctx.needs_input_grad[0] else None
+            dwl = torch.empty_like(wl)
+            dwr = torch.empty_like(wr)
+            dbl = torch.empty((HC,), device=dev, dtype=torch.float32)
+            dbr = torch.empty((HC,), device=dev, dtype=torch.float32)
+            ws2 = torch.empty((max(1, _lib.lib().tecgat_project_bwd_workspace(R, F, HC, impl)),), device=dev,
+                              dtype=torch.uint8)
+            _lib.call("tecgat_project_bwd", _ptr(dxl), _ptr(dxr), _ptr(x2d), _ptr(wl), _ptr(wr), _ptr(dx), _ptr(dwl),
+                      _ptr(dbl), _ptr(dwr), _ptr(dbr), _ptr(ws2), R, F, HC, dtype, impl, stream)
+        return (dx, dwl, dbl, dwr, dbr, datt, dbias) + (None,) * 10
+
+
+class _Linear(nn.Module):
+    """Parameter holder with ``torch_geometric.nn.dense.Linear``'s names (``weight``, ``bias``) and
+    init (glorot weight, U(+-1/sqrt(in)) bias)."""
+
+    def __init__(self, in_channels: int, out_channels: int):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.weight = nn.Parameter(torch.empty(out_channels, in_channels))
+        self.bias = nn.Parameter(torch.empty(out_channels))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        a = math.sqrt(6.0 / (self.weight.size(-2) + self.weight.size(-1)))
+        with torch.no_grad():
+            self.weight.uniform_(-a, a)
+            b = 1.0 / math.sqrt(self.in_channels)
+            self.bias.uniform_(-b, b)
+
+    def extra_repr(self):
+        return f"{self.in_channels}, {self.out_channels}, bias=True"
+
+
+class GATv2Conv(nn.Module):
+    """``GATv2Conv(in_channels, out_channels, heads=1, concat=True, negative_slope=0.2, dropout=0.0,
+    add_self_loops=True, edge_dim=None, fill_value='mean', bias=True, share_weights=False)``.
+
+    Only the configuration the reference uses is implemented in CUDA (``concat=True``,
+    ``add_self_loops=True``, ``edge_dim=None``, ``bias=True``, ``share_weights=False``); any other
+    value raises ``NotImplementedError`` instead of silently doing something else.
+    """
+
+    def __init__(self, in_channels: int, out_channels: int, heads: int = 1, concat: bool = True,
+                 negative_slope: float = 0.2, dropout: float = 0.0, add_self_loops: bool = True,
+                 edge_dim: Optional[int] = None, fill_value="mean", bias: bool = True,
+                 share_weights: bool = False, **kwargs):
+        super().__init__()
+        if kwargs:
+            raise NotImplementedError(f"GATv2Conv: unsupported arguments {sorted(kwargs)}")
+        if not isinstance(in_channels, int):
+            raise NotImplementedError("GATv2Conv: bipartite (tuple) in_channels are not supported")
+        if not concat or not add_self_loops or edge_dim is not None or not bias or share_weights:
+            raise NotImplementedError(
+                "GATv2Conv (tec_mollm_b200): only concat=True, add_self_loops=True, edge_dim=None, bias=True, "
+                "share_weights=False are implemented (the reference's configuration, modules.py:329-336)")
+        if not 0.0 <= dropout < 1.0:
+            raise ValueError(f"dropout must be in [0, 1); got {dropout}")
+        self.in_channels, self.out_channels, self.heads = in_channels, out_channels, heads
+        self.concat, self.negative_slope, self.dropout = concat, float(negative_slope), float(dropout)
+        self.add_self_loops, self.edge_dim, self.fill_value, self.share_weights = add_self_loops, edge_dim, fill_value, False
+        self.lin_l = _Linear(in_channels, heads * out_channels)
+        self.lin_r = _Linear(in_channels, heads * out_channels)
+        self.att = nn.Parameter(torch.empty(1, heads, out_channels))
+        self.bias = nn.Parameter(torch.empty(heads * out_channels))
+        self._plans = {}
+        self._tile_nodes = tile_nodes_for(heads)
+        self.reset_parameters()
+
+    def __getstate__(self):  # graph plans hold device handles: never pickled / deep-copied
+        state = self.__dict__.copy()
+        state["_plans"] = {}
+        return state
+
+    def reset_parameters(self):
+        self.lin_l.reset_parameters()
+        self.lin_r.reset_parameters()
+        a = math.sqrt(6.0 / (self.att.size(-2) + self.att.size(-1)))
+        with torch.no_grad():
+            self.att.uniform_(-a, a)
+            self.bias.zero_()
+
+    # ---- plan cache: the reference passes the same edge_index tensor every step (train.py:292-294, 388) ----
+    def plan_for(self, edge_index: torch.Tensor, num_nodes: int) -> GraphPlan:
+        key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape), int(num_nodes), edge_index.device)
+        hit = self._plans.get(key)
+        if hit is not None:
+            return hit[0]
+        plan = GraphPlan(edge_index, num_nodes, self._tile_nodes)
+        if len(self._plans) >= 8:
+            self._plans.pop(next(iter(self._plans)))
+        self._plans[key] = (plan, edge_index)  # keep the tensor alive so its data_ptr cannot be recycled
+        return plan
+
+    def _dropout_seed(self, device) -> int:
+        # drawn from torch's CPU generator: reproducible under torch.manual_seed, no device sync
+        return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+
+    def forward_snapshots(self, x: torch.Tensor, edge_index: torch.Tensor, snapshots: int, num_nodes: int,
+                          snapshot_mode: str = "shared", seed: Optional[int] = None) -> torch.Tensor:
+        """``x``: (snapshots*num_nodes, in_channels); the one-graph ``edge_index`` (indices < num_nodes) is
+        applied per ``snapshot_mode``.  Returns (snapshots*num_nodes, heads*out_channels) fp32."""
+        if not x.is_cuda:
+            raise RuntimeError("tec_mollm_b200.GATv2Conv: input must be a CUDA tensor (there is no CPU fallback)")
+        if x.dim() != 2 or x.size(1) != self.in_channels or x.size(0) != snapshots * num_nodes:
+            raise ValueError(f"x must be ({snapshots * num_nodes}, {self.in_channels}); got {tuple(x.shape)}")
+        if snapshot_mode not in ("shared", "literal"):
+            raise ValueError(f"snapshot_mode must be 'shared' or 'literal'; got {snapshot_mode!r}")
+        dtype = _lib.F32
+        if torch.is_autocast_enabled("cuda"):
+            ac = torch.get_autocast_dtype("cuda")
+            if ac != torch.bfloat16:
+                raise NotImplementedError(f"autocast dtype {ac} unsupported (bfloat16 only, train.py:68)")
+            dtype = _lib.BF16
+        x = x.contiguous()
+        if x.dtype != torch.float32:
+            x = x.float()
+        plan = self.plan_for(edge_index, num_nodes)
+        p = self.dropout if self.training else 0.0
+        if p > 0.0 and seed is None:
+            seed = self._dropout_seed(x.device)
+        mode = _lib.MODE_SHARED if snapshot_mode == "shared" else _lib.MODE_LITERAL
+        f32 = lambda t: t if t.dtype == torch.float32 else t.float()
+        return _GATv2Function.apply(
+            x, f32(self.lin_l.weight), f32(self.lin_l.bias), f32(self.lin_r.weight), f32(self.lin_r.bias),
+            f32(self.att), f32(self.bias), plan, int(snapshots), self.heads, self.out_channels,
+            self.negative_slope, float(p), int(seed or 0), mode, dtype, _proj_impl())
+
+    def forward(self, x: torch.Tensor, edge_index: torch.Tensor, edge_attr=None, return_attention_weights=None):
+        """PyG semantics for one 2-D input: ``num_nodes = x.size(0)`` rows, edges as given (so calling it the way
+        modules.py:356 does reproduces the reference literally)."""
+        if edge_attr is not None or return_attention_weights is not None:
+            raise NotImplementedError("GATv2Conv (tec_mollm_b200): edge_attr / return_attention_weights are not supported")
+        return self.forward_snapshots(x, edge_index, 1, x.size(0), "literal")
+
+    def __repr__(self):
+        return f"{self.__class__.__name__}({self.in_channels}, {self.out_channels}, heads={self.heads})"

@@ -1,0 +1,43 @@
+"""Drop-in ``SpatialEncoder`` (reference: ``src/model/modules.py:315-359``).
+
+Same constructor ``(in_channels, out_channels, heads=2, dropout=0.1)``, same attributes (``.gat_conv`` owning
+the PyG-named parameters, ``.output_channels``), same ``forward(x, edge_index, edge_weight=None)`` taking
+``x`` of shape ``(B*L, N, C_in)`` and returning ``(B*L, N, heads*out_channels)``.
+
+One extra keyword, ``snapshot_mode``: ``"shared"`` (default) applies the one-graph ``edge_index`` to every one of the
+``B*L`` snapshots -- the semantics the reference intends (tec_mollm.py:86-88) and BASELINE.json measures;
+``"literal"`` reproduces the call exactly as written (modules.py:353-356: the flattened ``(B*L*N, C)`` input meets an
+``edge_index`` whose indices are all ``< N``, so only snapshot 0 sees edges).
+"""
+from __future__ import annotations
+
+import logging
+
+import torch
+from torch import nn
+
+from .gatv2 import GATv2Conv
+
+
+class SpatialEncoder(nn.Module):
+    """Captures spatial dependencies using a GATv2 layer (hand-written sm_100a kernels)."""
+
+    def __init__(self, in_channels: int, out_channels: int, heads: int = 2, dropout: float = 0.1,
+                 snapshot_mode: str = "shared"):
+        super().__init__()
+        if snapshot_mode not in ("shared", "literal"):
+            raise ValueError(f"snapshot_mode must be 'shared' or 'literal'; got {snapshot_mode!r}")
+        self.gat_conv = GATv2Conv(in_channels, out_channels, heads=heads, dropout=dropout, concat=True,
+                                  add_self_loops=True)
+        self.output_channels = out_channels * heads
+        self.snapshot_mode = snapshot_mode
+        logging.info(f"SpatialEncoder initialized with out_channels={self.output_channels}")
+
+    def forward(self, x: torch.Tensor, edge_index: torch.Tensor, edge_weight: torch.Tensor = None) -> torch.Tensor:
+        # edge_weight is accepted and ignored, exactly like the reference (modules.py:347,355)
+        if x.dim() != 3:
+            raise ValueError(f"x must be (B*L, N, C_in); got {tuple(x.shape)}")
+        snapshots, num_nodes, in_channels = x.shape
+        x2d = x.reshape(-1, in_channels)
+        y = self.gat_conv.forward_snapshots(x2d, edge_index, snapshots, num_nodes, self.snapshot_mode)
+        return y.view(snapshots, num_nodes, self.output_channels)
