@@ -22,7 +22,8 @@
 namespace tg {
 
 constexpr int kTileM = 128;
-constexpr int kStages = 4;
+constexpr int kMaxStages = 4;
+constexpr uint32_t kSmemTwoCtas = 113 * 1024;  // dynamic shared memory that still lets two CTAs share an SM
 constexpr int kTcThreads = 192;
 
 struct TcFwdArgs {
@@ -33,6 +34,7 @@ struct TcFwdArgs {
     int32_t KP;  // K padded: multiple of 8 (tf32) / 16 (bf16)
     int32_t NP;  // N padded: multiple of 16
     int32_t acc_stride;  // TMEM columns between the two accumulator stages (power of two >= NP)
+    int32_t stages;      // depth of the x-tile ring (2..kMaxStages)
     int32_t tmem_cols;
 };
 
@@ -42,7 +44,7 @@ struct TcFwdSmem {  // byte offsets into dynamic shared memory
 };
 
 template <bool BF16>
-__host__ __device__ inline TcFwdSmem tc_fwd_smem(int F, int HC, int KP, int NP) {
+__host__ __device__ inline TcFwdSmem tc_fwd_smem(int F, int HC, int KP, int NP, int stages) {
     const uint32_t elem = BF16 ? 2 : 4;
     const uint32_t chunks = KP * elem / 16;  // 16-byte K chunks per row
     TcFwdSmem s;
@@ -58,7 +60,7 @@ __host__ __device__ inline TcFwdSmem tc_fwd_smem(int F, int HC, int KP, int NP) 
     s.a_hi = o; o += (kTileM / 8) * s.P_a;
     s.a_lo = o; o += BF16 ? 0 : (kTileM / 8) * s.P_a;
     s.stage_bytes = ((kTileM * F * 4 + 127) / 128) * 128;
-    s.xs = o; o += kStages * s.stage_bytes;
+    s.xs = o; o += stages * s.stage_bytes;
     const uint32_t out_bytes = ((kTileM * HC * elem + 127) / 128) * 128;
     s.out_l = o; o += out_bytes;
     s.out_r = o; o += out_bytes;
@@ -110,10 +112,11 @@ __global__ void __launch_bounds__(kTcThreads, 2) project_fwd_tc_kernel(const TcF
     extern __shared__ __align__(128) unsigned char smem[];
     using ST = typename std::conditional<BF16, __nv_bfloat16, float>::type;
     const int F = a.F, HC = a.HC, KP = a.KP, NP = a.NP;
-    const TcFwdSmem L = tc_fwd_smem<BF16>(F, HC, KP, NP);
+    const int kStages = a.stages;
+    const TcFwdSmem L = tc_fwd_smem<BF16>(F, HC, KP, NP, kStages);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bars);
-    uint64_t *x_full = bars, *x_empty = bars + kStages;
-    uint64_t *a_ready = bars + 2 * kStages, *a_free = a_ready + 1;
+    uint64_t *x_full = bars, *x_empty = bars + kMaxStages;
+    uint64_t *a_ready = bars + 2 * kMaxStages, *a_free = a_ready + 1;
     uint64_t *t_full = a_ready + 2, *t_empty = a_ready + 4;
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(smem + L.tmem_ptr);
     float *b_s = reinterpret_cast<float *>(smem + L.bias);
@@ -276,7 +279,7 @@ bool project_tc_supported(int F, int HC) {
     const int NP = ((2 * HC + 15) / 16) * 16;
     if (2 * pow2_cols(NP) > 256) return false;  // two CTAs per SM share the 512 TMEM columns
     const int KPt = ((F + 7) / 8) * 8;
-    return tc_fwd_smem<false>(F, HC, KPt, NP).total <= 110 * 1024;
+    return tc_fwd_smem<false>(F, HC, KPt, NP, 2).total <= 200 * 1024;
 }
 
 template <bool BF16>
@@ -285,7 +288,12 @@ static int launch_fwd_tc(TcFwdArgs &a, cudaStream_t st) {
     a.NP = ((2 * a.HC + 15) / 16) * 16;
     a.acc_stride = pow2_cols(a.NP);
     a.tmem_cols = 2 * a.acc_stride;
-    const TcFwdSmem L = tc_fwd_smem<BF16>(a.F, a.HC, a.KP, a.NP);
+    a.stages = kMaxStages;  // deepest ring that keeps two CTAs per SM; otherwise one CTA per SM with the full ring
+    while (a.stages > 2 && tc_fwd_smem<BF16>(a.F, a.HC, a.KP, a.NP, a.stages).total > kSmemTwoCtas) --a.stages;
+    if (tc_fwd_smem<BF16>(a.F, a.HC, a.KP, a.NP, a.stages).total > kSmemTwoCtas) a.stages = kMaxStages;
+    while (a.stages > 2 && tc_fwd_smem<BF16>(a.F, a.HC, a.KP, a.NP, a.stages).total > 200u * 1024u) --a.stages;
+    const TcFwdSmem L = tc_fwd_smem<BF16>(a.F, a.HC, a.KP, a.NP, a.stages);
+    TG_REQUIRE(L.total <= 200u * 1024u, TECGAT_ENOSUP, "project_fwd(tc): F=%d, HC=%d needs %u B shared memory", a.F, a.HC, L.total);
     auto kern = project_fwd_tc_kernel<BF16>;
     TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     const int64_t tiles = (a.R + kTileM - 1) / kTileM;

@@ -41,6 +41,18 @@ def tile_nodes_for(heads: int) -> int:
     return max(8, min(128, (t // 8) * 8))
 
 
+# Optional per-phase instrumentation used by bench.py: when set to a list, a CUDA event is recorded on the launching
+# stream after every phase ("proj_fwd", "edge_fwd", "edge_bwd", "proj_bwd"); None (default) costs nothing.
+PHASE_EVENTS = None
+
+
+def _mark(name: str, device):
+    if PHASE_EVENTS is not None:
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(torch.cuda.current_stream(device))
+        PHASE_EVENTS.append((name, ev))
+
+
 def _proj_impl() -> int:
     """Tensor-core projections are the product path; ``TECGAT_PROJ=ffma`` selects the CUDA-core
     cross-check kernels (tests only)."""
@@ -108,13 +120,16 @@ class _GATv2Function(torch.autograd.Function):
             stream = _stream(dev)
             xl = torch.empty((R, HC), device=dev, dtype=st_dtype)
             xr = torch.empty((R, HC), device=dev, dtype=st_dtype)
-            _lib.call("tecgat_project_fwd", _ptr(x2d), _ptr(wl), _ptr(bl), _ptr(wr), _ptr(br), _ptr(xl), _ptr(xr),
-                      R, F, HC, dtype, impl, stream)
             y = torch.empty((R, HC), device=dev, dtype=torch.float32)
             m = torch.empty((R, H), device=dev, dtype=torch.float32)
             den = torch.empty((R, H), device=dev, dtype=torch.float32)
+            _mark("start_fwd", dev)
+            _lib.call("tecgat_project_fwd", _ptr(x2d), _ptr(wl), _ptr(bl), _ptr(wr), _ptr(br), _ptr(xl), _ptr(xr),
+                      R, F, HC, dtype, impl, stream)
+            _mark("proj_fwd", dev)
             _lib.call("tecgat_edge_fwd", plan.handle, _ptr(xl), _ptr(xr), _ptr(att), _ptr(bias), _ptr(y), _ptr(m),
                       _ptr(den), S, H, Cc, slope, p, seed, mode, dtype, stream)
+            _mark("edge_fwd", dev)
         ctx.save_for_backward(x2d, wl, wr, att, bias, xl, xr, y, m, den)
         ctx.plan = plan
         ctx.cfg = (S, H, Cc, slope, p, seed, mode, dtype, impl)
@@ -139,9 +154,6 @@ class _GATv2Function(torch.autograd.Function):
             dbias = torch.empty((HC,), device=dev, dtype=torch.float32)
             ws1 = torch.empty((max(1, _lib.lib().tecgat_edge_bwd_workspace(plan.handle, S, H, Cc)),), device=dev,
                               dtype=torch.uint8)
-            _lib.call("tecgat_edge_bwd", plan.handle, _ptr(xl), _ptr(xr), _ptr(att), _ptr(bias), _ptr(y), _ptr(m),
-                      _ptr(den), _ptr(gy), _ptr(dxl), _ptr(dxr), _ptr(datt), _ptr(dbias), _ptr(ws1), S, H, Cc, slope, p,
-                      seed, mode, dtype, stream)
             dx = torch.empty_like(x2d) if ctx.needs_input_grad[0] else None
             dwl = torch.empty_like(wl)
             dwr = torch.empty_like(wr)
@@ -149,8 +161,14 @@ class _GATv2Function(torch.autograd.Function):
             dbr = torch.empty((HC,), device=dev, dtype=torch.float32)
             ws2 = torch.empty((max(1, _lib.lib().tecgat_project_bwd_workspace(R, F, HC, impl)),), device=dev,
                               dtype=torch.uint8)
+            _mark("start_bwd", dev)
+            _lib.call("tecgat_edge_bwd", plan.handle, _ptr(xl), _ptr(xr), _ptr(att), _ptr(bias), _ptr(y), _ptr(m),
+                      _ptr(den), _ptr(gy), _ptr(dxl), _ptr(dxr), _ptr(datt), _ptr(dbias), _ptr(ws1), S, H, Cc, slope, p,
+                      seed, mode, dtype, stream)
+            _mark("edge_bwd", dev)
             _lib.call("tecgat_project_bwd", _ptr(dxl), _ptr(dxr), _ptr(x2d), _ptr(wl), _ptr(wr), _ptr(dx), _ptr(dwl),
                       _ptr(dbl), _ptr(dwr), _ptr(dbr), _ptr(ws2), R, F, HC, dtype, impl, stream)
+            _mark("proj_bwd", dev)
         return (dx, dwl, dbl, dwr, dbr, datt, dbias) + (None,) * 10
 
 

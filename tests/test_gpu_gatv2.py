@@ -1,0 +1,325 @@
+"""GPU parity tests (run with `-m gpu` on the B200): CUDA path through the C ABI vs the CPU oracle.
+
+Tolerances are BASELINE.json's: fp32 outputs and gradients <= 1e-5 relative (max |diff| / max |ref|, against the
+fp64 oracle), bf16-autocast <= 1e-2 (against the oracle run under CPU autocast, i.e. PyG's dtype flow)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import kernel_dropout_mask, load_golden, random_graph, rel_err
+from oracle import gatv2_oracle as G
+from oracle import graph_oracle as go
+
+pytestmark = pytest.mark.gpu
+
+TOL_F32 = 1e-5
+TOL_BF16 = 1e-2
+
+
+def _encoder(F, H, C, params, device, mode="shared", dropout=0.0):
+    from tec_mollm_b200 import SpatialEncoder
+
+    enc = SpatialEncoder(F, C, heads=H, dropout=dropout, snapshot_mode=mode).to(device)
+    sd = {f"gat_conv.{k}": v.float() for k, v in params.items()}
+    enc.load_state_dict(sd, strict=True)
+    return enc
+
+
+def _run_cuda(enc, x, ei, gy, autocast=False, seed=None):
+    dev = next(enc.parameters()).device
+    xg = x.float().to(dev).requires_grad_(True)
+    enc.zero_grad(set_to_none=True)
+    if autocast:
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y = enc(xg, ei.to(dev))
+    else:
+        y = enc(xg, ei.to(dev))
+    y.backward(gy.float().to(dev))
+    grads = {"x": xg.grad}
+    grads.update({k[len("gat_conv."):]: p.grad for k, p in enc.named_parameters()})
+    return y.detach(), grads
+
+
+def _check(y, grads, y_ref, g_ref, tol, what=""):
+    assert y.dtype == torch.float32
+    e = rel_err(y, y_ref)
+    assert e <= tol, f"{what} y: rel err {e:.3e} > {tol}"
+    for k, ref in g_ref.items():
+        e = rel_err(grads[k], ref)
+        assert e <= tol, f"{what} grad {k}: rel err {e:.3e} > {tol}"
+
+
+def _rand_case(S, N, F, H, C, seed, dtype=torch.float64):
+    gen = torch.Generator().manual_seed(seed)
+    x = torch.randn(S, N, F, generator=gen, dtype=dtype)
+    gy = torch.randn(S, N, H * C, generator=gen, dtype=dtype)
+    p = G.init_params(F, C, H, seed=seed + 1, dtype=dtype)
+    p["bias"] = torch.randn(H * C, generator=gen, dtype=dtype) * 0.1
+    return x, gy, p
+
+
+# ---------------------------------------------------------------------------------------------------------
+# plan
+# ---------------------------------------------------------------------------------------------------------
+def test_plan_matches_pyg_edge_surgery(cuda_device):
+    from tec_mollm_b200 import GraphPlan
+
+    N = 50
+    ei = random_graph(N, 300, seed=0, isolated=(7, 49))
+    plan = GraphPlan(ei.to(cuda_device), N, 32)
+    rowptr, col, eid = plan.export()
+    ref = G.remove_then_add_self_loops(ei, N)
+    assert plan.num_edges == ref.size(1) and plan.kept_edges == ref.size(1) - N
+    src, dst = ref[0].numpy(), ref[1].numpy()
+    assert sorted(eid.tolist()) == list(range(ref.size(1)))          # a permutation of PyG's edge ids
+    for i in range(N):
+        ids = eid[rowptr[i]:rowptr[i + 1]]
+        assert np.all(dst[ids] == i)                                  # destination-sorted
+        assert np.array_equal(col[rowptr[i]:rowptr[i + 1]], src[ids])
+        assert np.all(np.diff(ids) > 0)                               # stable: PyG's per-destination order
+        assert ids[-1] == plan.kept_edges + i                         # the self loop is last
+    assert plan.max_in_degree == int(np.diff(rowptr).max())
+
+
+def test_plan_rejects_bad_input(cuda_device):
+    from tec_mollm_b200 import GraphPlan
+
+    with pytest.raises(RuntimeError, match="outside"):
+        GraphPlan(torch.tensor([[0, 9], [1, 2]], device=cuda_device), 5, 32)
+    with pytest.raises(ValueError):
+        GraphPlan(torch.zeros(3, 4, dtype=torch.int64, device=cuda_device), 5, 32)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        GraphPlan(torch.tensor([[0], [1]]), 5, 32)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# projections: tensor-core path vs CUDA-core path vs fp64 matmul
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("impl", ["ffma", "tc"])
+@pytest.mark.parametrize("R,F,HC", [(1000, 22, 22), (128 * 5, 10, 10), (77, 22, 44), (2911 * 3, 22, 22), (300, 7, 6)])
+def test_projection_forward(cuda_device, impl, R, F, HC):
+    from tec_mollm_b200 import _lib
+
+    gen = torch.Generator().manual_seed(R + F)
+    x = torch.randn(R, F, generator=gen)
+    wl, wr = torch.randn(HC, F, generator=gen) * 0.3, torch.randn(HC, F, generator=gen) * 0.3
+    bl, br = torch.randn(HC, generator=gen), torch.randn(HC, generator=gen)
+    d = lambda t: t.to(cuda_device)
+    xl = torch.full((R, HC), float("nan"), device=cuda_device)
+    xr = torch.full((R, HC), float("nan"), device=cuda_device)
+    code = _lib.PROJ_TC if impl == "tc" else _lib.PROJ_FFMA
+    xd, wld, bld, wrd, brd = d(x), d(wl), d(bl), d(wr), d(br)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    _lib.call("tecgat_project_fwd", p(xd), p(wld), p(bld), p(wrd), p(brd), p(xl), p(xr), R, F, HC, _lib.F32, code,
+              C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    ref_l = x.double() @ wl.double().t() + bl.double()
+    ref_r = x.double() @ wr.double().t() + br.double()
+    assert rel_err(xl, ref_l) <= 2e-6, f"xl {rel_err(xl, ref_l):.3e}"
+    assert rel_err(xr, ref_r) <= 2e-6, f"xr {rel_err(xr, ref_r):.3e}"
+    # bf16 contract
+    xl16 = torch.empty((R, HC), device=cuda_device, dtype=torch.bfloat16)
+    xr16 = torch.empty((R, HC), device=cuda_device, dtype=torch.bfloat16)
+    _lib.call("tecgat_project_fwd", p(xd), p(wld), p(bld), p(wrd), p(brd), p(xl16), p(xr16), R, F, HC, _lib.BF16, code,
+              C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert rel_err(xl16.float(), ref_l) <= 1e-2 and rel_err(xr16.float(), ref_r) <= 1e-2
+
+
+# ---------------------------------------------------------------------------------------------------------
+# fused path vs oracle
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["f22h2c11", "f10h2c5", "f22h4c11"])
+@pytest.mark.parametrize("mode", ["shared", "literal"])
+def test_golden_fixtures_fp32(cuda_device, name, mode):
+    g = load_golden(f"gatv2_{name}.npz")
+    F, H, Cc = int(g["F"]), int(g["H"]), int(g["C"])
+    params = {k: torch.from_numpy(g[f"p_{k}"]) for k in G.PARAM_NAMES}
+    x, gy, ei = torch.from_numpy(g["x"]), torch.from_numpy(g["gy"]), torch.from_numpy(g["edge_index"])
+    enc = _encoder(F, H, Cc, params, cuda_device, mode).eval()
+    y, grads = _run_cuda(enc, x, ei, gy)
+    y_ref = torch.from_numpy(g[f"y_{mode}"])
+    g_ref = {k: torch.from_numpy(g[f"g_{mode}_{k}"]) for k in ("x",) + G.PARAM_NAMES}
+    _check(y, grads, y_ref, g_ref, TOL_F32, f"{name}/{mode}")
+
+
+@pytest.mark.parametrize("S,N,F,H,C,E", [
+    (3, 40, 7, 2, 5, 200),      # duplicates, self loops, isolated node, asymmetric
+    (2, 300, 22, 2, 11, 3000),  # several tiles, window larger than a tile
+    (1, 17, 6, 1, 8, 60),       # single head, even C
+    (4, 90, 5, 4, 3, 500),      # four heads
+    (2, 64, 9, 2, 16, 400),
+    (2, 33, 4, 3, 4, 150),      # heads not a power of two
+])
+def test_random_graphs_fp32(cuda_device, S, N, F, H, C, E):
+    ei = random_graph(N, E, seed=N + E, isolated=(3,))
+    x, gy, p = _rand_case(S, N, F, H, C, seed=S * 100 + N)
+    enc = _encoder(F, H, C, p, cuda_device).eval()
+    y, grads = _run_cuda(enc, x, ei, gy)
+    y_ref, g_ref = G.fwd_bwd(x, ei, p, H, C, gy)
+    _check(y, grads, y_ref, g_ref, TOL_F32, f"S{S}N{N}F{F}H{H}C{C}")
+
+
+def test_empty_edge_list_and_single_node(cuda_device):
+    """No edges at all: every node attends only to its self loop (y = W_l x + b_l + bias)."""
+    S, N, F, H, C = 2, 9, 5, 2, 3
+    x, gy, p = _rand_case(S, N, F, H, C, seed=1)
+    ei = torch.zeros(2, 0, dtype=torch.int64)
+    enc = _encoder(F, H, C, p, cuda_device).eval()
+    y, grads = _run_cuda(enc, x, ei, gy)
+    y_ref, g_ref = G.fwd_bwd(x, ei, p, H, C, gy)
+    _check(y, grads, y_ref, g_ref, TOL_F32, "empty")
+    x1, gy1, _ = _rand_case(1, 1, F, H, C, seed=2)
+    y, grads = _run_cuda(enc, x1, ei, gy1)
+    y_ref, g_ref = G.fwd_bwd(x1, ei, p, H, C, gy1)
+    _check(y, grads, y_ref, g_ref, TOL_F32, "single node")
+
+
+def test_reference_graph_fp32_and_determinism(cuda_device):
+    """The 2911-node, 150 km graph (reference golden edge list), default shape F=22, H=2, C=11."""
+    g = load_golden("graph_cn150.npz")
+    ei = torch.from_numpy(g["edge_index"])
+    S, N, F, H, C = 4, 2911, 22, 2, 11
+    x, gy, p = _rand_case(S, N, F, H, C, seed=5)
+    enc = _encoder(F, H, C, p, cuda_device).eval()
+    y, grads = _run_cuda(enc, x, ei, gy)
+    y_ref, g_ref = G.fwd_bwd(x, ei, p, H, C, gy)
+    _check(y, grads, y_ref, g_ref, TOL_F32, "cn150")
+    y2, grads2 = _run_cuda(enc, x, ei, gy)
+    assert torch.equal(y, y2)                                   # atomic-free => bit-reproducible
+    for k in grads:
+        assert torch.equal(grads[k], grads2[k]), k
+
+
+def test_dense_graph_four_heads(cuda_device):
+    """BASELINE config 4: 300 km graph (76,532 edges, max degree 38), H=4, C=11."""
+    g = load_golden("graph_cn300.npz")
+    ei = torch.from_numpy(g["edge_index"])
+    S, N, F, H, C = 2, 2911, 22, 4, 11
+    x, gy, p = _rand_case(S, N, F, H, C, seed=6)
+    enc = _encoder(F, H, C, p, cuda_device).eval()
+    y, grads = _run_cuda(enc, x, ei, gy)
+    y_ref, g_ref = G.fwd_bwd(x, ei, p, H, C, gy)
+    _check(y, grads, y_ref, g_ref, TOL_F32, "cn300/h4")
+
+
+@pytest.mark.parametrize("mode", ["shared", "literal"])
+def test_dropout_with_the_kernels_own_mask(cuda_device, mode):
+    """Training-mode attention dropout: the oracle is fed exactly the keep-mask the kernels derive from
+    (seed, snapshot, CSR slot, head), so forward AND backward must agree to fp32 tolerance."""
+    S, N, F, H, C, p_drop = 3, 60, 22, 2, 11, 0.25
+    ei = random_graph(N, 400, seed=12)
+    x, gy, p = _rand_case(S, N, F, H, C, seed=13)
+    enc = _encoder(F, H, C, p, cuda_device, mode, dropout=p_drop).train()
+    seed = 987654321
+    enc.gat_conv._dropout_seed = lambda device: seed
+    y, grads = _run_cuda(enc, x, ei, gy)
+    plan = next(iter(enc.gat_conv._plans.values()))[0]
+    mask = kernel_dropout_mask(plan, S, H, p_drop, seed, mode).double()
+    assert 0.15 < 1.0 - mask.mean().item() < 0.35
+    y_ref, g_ref = G.fwd_bwd(x, ei, p, H, C, gy, snapshot_mode=mode, edge_mask=mask, p=p_drop)
+    _check(y, grads, y_ref, g_ref, TOL_F32, f"dropout/{mode}")
+    enc.eval()
+    y_eval, _ = _run_cuda(enc, x, ei, gy)
+    y_ref0, _ = G.fwd_bwd(x, ei, p, H, C, gy, snapshot_mode=mode)
+    assert rel_err(y_eval, y_ref0) <= TOL_F32                   # eval() disables dropout
+
+
+@pytest.mark.parametrize("S,N,F,H,C,E", [(3, 63, 22, 2, 11, 0), (2, 200, 10, 2, 5, 1500)])
+def test_bf16_autocast(cuda_device, S, N, F, H, C, E):
+    """bf16-autocast contract (train.py:68).  The forward must sit within 1e-2 of PyG's dtype flow (the oracle run under
+    CPU autocast).  PyG's autocast BACKWARD accumulates the gathered gradients in bf16 and is itself 4-15 % away from the
+    fp64 truth (measured: lin_r.weight 0.15), so for gradients the gate is the truth: ours must be within 1e-2 of fp64,
+    or at least as close to it as PyG-autocast is, and never further from PyG-autocast than PyG-autocast is from truth."""
+    if E == 0:
+        ei = torch.from_numpy(load_golden("graph_small150.npz")["edge_index"])
+    else:
+        ei = random_graph(N, E, seed=21)
+    x, gy, p = _rand_case(S, N, F, H, C, seed=22, dtype=torch.float32)
+    enc = _encoder(F, H, C, p, cuda_device).eval()
+    y, grads = _run_cuda(enc, x, ei, gy, autocast=True)
+    y_ac, g_ac = G.fwd_bwd(x, ei, p, H, C, gy, autocast_bf16=True)       # PyG's dtype flow on CPU
+    y64, g64 = G.fwd_bwd(x.double(), ei, {k: v.double() for k, v in p.items()}, H, C, gy.double())
+    assert y.dtype == torch.float32
+    e = rel_err(y, y_ac)
+    assert e <= TOL_BF16, f"y vs autocast oracle: {e:.3e}"
+    assert rel_err(y, y64) <= TOL_BF16
+    for k in g64:
+        ours, theirs = rel_err(grads[k], g64[k]), rel_err(g_ac[k], g64[k])
+        print(f"bf16 grad {k}: ours vs fp64 {ours:.3e}; PyG-autocast vs fp64 {theirs:.3e}")
+        assert ours <= max(TOL_BF16, theirs), f"grad {k}: {ours:.3e} (PyG-autocast itself: {theirs:.3e})"
+        assert rel_err(grads[k], g_ac[k]) <= max(TOL_BF16, 2.0 * theirs), k
+
+
+def test_full_size_properties(cuda_device):
+    """BASELINE config 1 size (B=2 x 48 snapshots x 2911 nodes): size-independent properties instead of a full oracle run.
+    (1) snapshot permutation equivariance, bit-exact; (2) a replicated snapshot gives replicated outputs and input grads;
+    (3) parameter gradients add over snapshot shards; (4) oracle parity on a random subset of snapshots."""
+    g = load_golden("graph_cn150.npz")
+    ei = torch.from_numpy(g["edge_index"])
+    S, N, F, H, C = 96, 2911, 22, 2, 11
+    x, gy, p = _rand_case(S, N, F, H, C, seed=31, dtype=torch.float32)
+    enc = _encoder(F, H, C, p, cuda_device).eval()
+    y, grads = _run_cuda(enc, x, ei, gy)
+    perm = torch.randperm(S, generator=torch.Generator().manual_seed(1))
+    y_p, grads_p = _run_cuda(enc, x[perm], ei, gy[perm])
+    assert torch.equal(y_p.cpu(), y.cpu()[perm])
+    assert torch.equal(grads_p["x"].cpu(), grads["x"].cpu()[perm])
+    xr = x.clone(); xr[1] = xr[0]
+    gr = gy.clone(); gr[1] = gr[0]
+    y_r, grads_r = _run_cuda(enc, xr, ei, gr)
+    assert torch.equal(y_r[0], y_r[1]) and torch.equal(grads_r["x"][0], grads_r["x"][1])
+    half = S // 2
+    _, ga = _run_cuda(enc, x[:half], ei, gy[:half])
+    ga = {k: v.clone() for k, v in ga.items()}
+    _, gb = _run_cuda(enc, x[half:], ei, gy[half:])
+    for k in G.PARAM_NAMES:
+        assert rel_err(ga[k] + gb[k], grads[k]) <= 2e-6, k
+    sub = [0, 17, 95]
+    y_ref, g_ref = G.fwd_bwd(x[sub].double(), ei, {k: v.double() for k, v in p.items()}, H, C, gy[sub].double())
+    assert rel_err(y.cpu()[sub], y_ref) <= TOL_F32
+    assert rel_err(grads["x"].cpu()[sub], g_ref["x"]) <= TOL_F32
+
+
+def test_gatv2conv_direct_call_is_pyg_semantics(cuda_device):
+    """GATv2Conv.forward(x2d, edge_index) on the flattened input == the reference's literal call (modules.py:356)."""
+    from tec_mollm_b200 import GATv2Conv
+
+    S, N, F, H, C = 3, 30, 8, 2, 4
+    ei = random_graph(N, 120, seed=40)
+    x, gy, p = _rand_case(S, N, F, H, C, seed=41)
+    conv = GATv2Conv(F, C, heads=H, dropout=0.0, concat=True, add_self_loops=True).to(cuda_device).eval()
+    conv.load_state_dict({k: v.float() for k, v in p.items()}, strict=True)
+    y = conv(x.reshape(-1, F).float().to(cuda_device), ei.to(cuda_device))
+    y_ref = G.spatial_encoder_forward(x, ei, p, H, C, "literal").reshape(-1, H * C)
+    assert rel_err(y, y_ref) <= TOL_F32
+
+
+def test_works_inside_grad_scaler_and_optimizer_step(cuda_device):
+    """train.py:68-110 shape of use: autocast + GradScaler + AdamW step; loss must go down on a toy target."""
+    from tec_mollm_b200 import SpatialEncoder
+
+    torch.manual_seed(0)
+    S, N, F, H, C = 4, 63, 22, 2, 11
+    ei = torch.from_numpy(load_golden("graph_small150.npz")["edge_index"]).to(cuda_device)
+    enc = SpatialEncoder(F, C, heads=H, dropout=0.1).to(cuda_device).train()
+    opt = torch.optim.AdamW(enc.parameters(), lr=1e-2)
+    scaler = torch.amp.GradScaler("cuda")
+    x = torch.randn(S, N, F, device=cuda_device)
+    target = torch.randn(S, N, H * C, device=cuda_device)
+    losses = []
+    for _ in range(30):
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = x + enc(x, ei)                                  # the residual of tec_mollm.py:94
+            loss = torch.nn.functional.huber_loss(out, target)
+        scaler.scale(loss).backward()
+        scaler.unscale_(opt)
+        torch.nn.utils.clip_grad_norm_(enc.parameters(), 1.0)
+        scaler.step(opt)
+        scaler.update()
+        losses.append(loss.item())
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0]
