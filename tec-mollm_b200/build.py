@@ -36,11 +36,16 @@ def _nvcc() -> str:
     return exe
 
 
-def _stale(target: str, deps) -> bool:
-    if not os.path.exists(target):
-        return True
-    t = os.path.getmtime(target)
-    return any(os.path.getmtime(d) > t for d in deps)
+def _digest(paths) -> str:
+    """Content hash of the sources (mtimes do not survive the snapshot to the GPU box)."""
+    import hashlib
+
+    h = hashlib.sha256(" ".join(NVCC_FLAGS[:8]).encode())
+    for p in sorted(paths):
+        h.update(os.path.basename(p).encode())
+        with open(p, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -48,17 +53,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
     headers = sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + sorted(glob.glob(os.path.join(ROOT, "include", "*.h")))
     if not sources:
         raise RuntimeError(f"no CUDA sources under {CSRC}")
+    stamp = LIB + ".sha256"
+    want = _digest(sources + headers)
+    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == want:
+        return LIB  # up to date
     os.makedirs(OBJ_DIR, exist_ok=True)
     os.makedirs(LIB_DIR, exist_ok=True)
     nvcc = _nvcc()
-    jobs = []
-    for src in sources:
-        obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
-        if force or _stale(obj, [src] + headers + [os.path.abspath(__file__)]):
-            jobs.append((src, obj))
 
-    def compile_one(job):
-        src, obj = job
+    def compile_one(src):
+        obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
         cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
@@ -67,15 +71,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(r.stderr)
         return obj
 
-    if jobs:
-        with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
-            list(ex.map(compile_one, jobs))
-    objs = [os.path.join(OBJ_DIR, os.path.basename(s)[:-3] + ".o") for s in sources]
-    if force or jobs or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-cudart", "static"]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        if r.returncode != 0:
-            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    with ThreadPoolExecutor(max_workers=min(8, len(sources))) as ex:
+        objs = list(ex.map(compile_one, sources))
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-cudart", "static"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    with open(stamp, "w") as f:
+        f.write(want)
     return LIB
 
 
