@@ -159,7 +159,14 @@ def spatial_encoder_forward(x: torch.Tensor, edge_index: torch.Tensor, params: D
 # and to document the formulas the CUDA backward implements
 # --------------------------------------------------------------------------
 def gatv2_backward_manual(x, edge_index, params, heads, out_channels, grad_y,
-                          negative_slope: float = 0.2, edge_mask=None, p: float = 0.0):
+                          negative_slope: float = 0.2, edge_mask=None, p: float = 0.0, pos_mask=None,
+                          return_preact: bool = False):
+    """Closed-form gradients.  ``pos_mask`` (E, H, C) bool, optional, overrides the LeakyReLU branch decision
+    ``s > 0`` used for the DERIVATIVE (the forward value is continuous and keeps its own sign): the gradient of GATv2 is
+    discontinuous where a pre-activation ``s = xl_j + xr_i`` crosses zero, and when ``|s|`` is below the fp32 resolution
+    of ``xl``/``xr`` any fp32 implementation (PyG's included) picks the branch its own rounding dictates.  The GPU tests
+    pass the branch decisions implied by the kernels' own fp32 ``xl``/``xr`` and separately assert that they differ from
+    the fp64 decisions only where ``|s|`` is tiny."""
     nn_rows = x.size(0)
     H, C = heads, out_channels
     Wl, bl, Wr, br = params["lin_l.weight"], params["lin_l.bias"], params["lin_r.weight"], params["lin_r.bias"]
@@ -182,12 +189,18 @@ def gatv2_backward_manual(x, edge_index, params, heads, out_channels, grad_y,
     delta = (g * out).sum(-1)                                            # (Nn, H): g_i . out_i
     gx = (g[dst] * xl[src]).sum(-1)                                      # (E, H)
     de = alpha * (q * gx - delta[dst])
-    ds = de.unsqueeze(-1) * att * torch.where(s > 0, torch.ones_like(s), torch.full_like(s, negative_slope))
+    pos = (s > 0) if pos_mask is None else pos_mask
+    ds = de.unsqueeze(-1) * att * torch.where(pos, torch.ones_like(s), torch.full_like(s, negative_slope))
     d_att = (de.unsqueeze(-1) * z).sum(0, keepdim=True)
     d_xl = torch.zeros_like(xl).index_add(0, src, (alpha * q).unsqueeze(-1) * g[dst] + ds)
     d_xr = torch.zeros_like(xr).index_add(0, dst, ds)
     d_xl2, d_xr2 = d_xl.view(nn_rows, H * C), d_xr.view(nn_rows, H * C)
+    y = out.view(nn_rows, H * C) + params["bias"]
+    extra = {"y": y, "d_xl": d_xl2, "d_xr": d_xr2}
+    if return_preact:
+        extra.update({"s": s, "edges": ei})
     return {
+        "_extra": extra,
         "x": d_xl2 @ Wl + d_xr2 @ Wr,
         "lin_l.weight": d_xl2.t() @ x, "lin_l.bias": d_xl2.sum(0),
         "lin_r.weight": d_xr2.t() @ x, "lin_r.bias": d_xr2.sum(0),
