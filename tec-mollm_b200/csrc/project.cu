@@ -10,7 +10,9 @@ extern "C" int tecgat_project_fwd(const float *x, const float *wl, const float *
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (impl == TECGAT_PROJ_FFMA) return tg::project_fwd_ffma(x, wl, bl, wr, br, xl, xr, rows, F, hc, dtype, st);
     TG_REQUIRE(impl == TECGAT_PROJ_TC, TECGAT_EINVAL, "project_fwd: bad impl %d", impl);
-    TG_REQUIRE(tg::project_tc_supported(F, hc), TECGAT_ENOSUP, "project_fwd(tc): in_channels=%d, heads*out_channels=%d outside the tensor-core kernel's range", F, hc);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(xl) | reinterpret_cast<uintptr_t>(xr)) & 15) == 0;
+    if (!aligned || !tg::project_tc_supported(F, hc))  // shapes / alignments outside the tensor-core kernel's range
+        return tg::project_fwd_ffma(x, wl, bl, wr, br, xl, xr, rows, F, hc, dtype, st);
     return tg::project_fwd_tc(x, wl, bl, wr, br, xl, xr, rows, F, hc, dtype, st);
 }
 
@@ -29,6 +31,5 @@ extern "C" int tecgat_project_bwd(const void *dxl, const void *dxr, const float 
     if (impl == TECGAT_PROJ_FFMA)
         return tg::project_bwd_ffma(dxl, dxr, x, wl, wr, dx, dwl, dbl, dwr, dbr, workspace, rows, F, hc, dtype, st);
     TG_REQUIRE(impl == TECGAT_PROJ_TC, TECGAT_EINVAL, "project_bwd: bad impl %d", impl);
-    TG_REQUIRE(tg::project_tc_supported(F, hc), TECGAT_ENOSUP, "project_bwd(tc): in_channels=%d, heads*out_channels=%d outside the tensor-core kernel's range", F, hc);
     return tg::project_bwd_tc(dxl, dxr, x, wl, wr, dx, dwl, dbl, dwr, dbr, workspace, rows, F, hc, dtype, st);
 }

@@ -17,6 +17,7 @@
 #include <type_traits>
 
 #include "project.cuh"
+#include "reduce.cuh"
 #include "tc.cuh"
 
 namespace tg {
@@ -314,13 +315,336 @@ int project_fwd_tc(const float *x, const float *wl, const float *bl, const float
     return dtype == TECGAT_BF16 ? launch_fwd_tc<true>(a, st) : launch_fwd_tc<false>(a, st);
 }
 
-// ---- backward: tensor-core version lands next; until then the C ABI routes TC requests for the backward to the
-//      CUDA-core kernels (same results, checked by the same tests) ------------------------------------------------------
-int64_t project_bwd_tc_workspace(int64_t R, int F, int HC) { return project_bwd_ffma_workspace(R, F, HC); }
+// =====================================================================================================================
+// backward:  dx = [dxl | dxr] [Wl; Wr]            (GEMM1: M = rows, K = 2*H*C, N = in_channels)
+//            [dWl; dWr | dbl; dbr] = [dxl | dxr]^T [x | 1]   (GEMM2: M = 2*H*C, K = rows, N = in_channels + 1)
+// One pass over dxl, dxr, x.  The row tile of [dxl | dxr] is laid out ONCE in shared memory (canonical layout, tc.cuh) and
+// read twice by the tensor core: as the K-major A operand of GEMM1 and as the MN-major A operand of GEMM2 -- no
+// transposition pass.  The x tile gets a constant-one column, so the bias gradients fall out of GEMM2 for free.
+// GEMM2 accumulates in TMEM across all the CTA's tiles; per-CTA partials + the fixed-order fp64 second stage
+// (reduce.cu) keep the parameter gradients deterministic.  fp32 contract: 3xTF32 on both GEMMs.
+// CTA = 10 warps, one per SM: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-9 = workers (two threads per row: one
+// re-lays the gradient row, the other the x row; they split the epilogue columns).
+// =====================================================================================================================
+constexpr int kBwdThreads = 320;
+constexpr int kBwdWorkers = 256;
+constexpr int kBwdMaxStages = 3;
+
+struct TcBwdArgs {
+    const void *dxl, *dxr;
+    const float *x, *wl, *wr;
+    float *dx;        // may be NULL (input does not require grad): GEMM1 is skipped
+    float *partials;  // (grid, 2*HC*F + 2*HC): [dWl | dWr | dbl | dbr] per CTA
+    int64_t R;
+    int32_t F, HC;
+    int32_t OP;   // 2*HC padded to the MMA K granularity (8 tf32 / 16 bf16)
+    int32_t N1;   // F padded to 16 (GEMM1 N)
+    int32_t NP2;  // F + 1 padded to 16 (GEMM2 N)
+    int32_t d1_stride, d2_col, tmem_cols, stages;
+};
+
+struct TcBwdSmem {
+    uint32_t bars, tmem_ptr, w_hi, w_lo, d_hi, d_lo, x_hi, x_lo, stage0, dx_st, total;
+    uint32_t P_w, P_d, P_x, tile_d, tile_x, stage_bytes;
+};
+
+template <bool BF16>
+__host__ __device__ inline TcBwdSmem tc_bwd_smem(int F, int HC, int OP, int N1, int NP2, int stages) {
+    const uint32_t elem = BF16 ? 2 : 4, epc = 16 / elem;
+    TcBwdSmem s;
+    uint32_t o = 0;
+    s.bars = o; o += 256;
+    s.tmem_ptr = o; o += 128;
+    s.P_w = (OP / epc) * 128; s.P_d = (OP / epc) * 128; s.P_x = (NP2 / epc) * 128;
+    s.w_hi = o; o += (N1 / 8) * s.P_w;
+    s.w_lo = o; o += BF16 ? 0 : (N1 / 8) * s.P_w;
+    s.d_hi = o; o += (kTileM / 8) * s.P_d;
+    s.d_lo = o; o += BF16 ? 0 : (kTileM / 8) * s.P_d;
+    s.x_hi = o; o += (kTileM / 8) * s.P_x;   // also absorbs the MN-major over-read of the gradient operand (see kernel)
+    s.x_lo = o; o += BF16 ? 0 : (kTileM / 8) * s.P_x;
+    s.tile_d = ((kTileM * HC * elem + 127) / 128) * 128;
+    s.tile_x = ((kTileM * F * 4 + 127) / 128) * 128;
+    s.stage_bytes = 2 * s.tile_d + s.tile_x;
+    s.stage0 = o; o += stages * s.stage_bytes;
+    s.dx_st = o; o += s.tile_x;
+    s.total = o;
+    return s;
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(kBwdThreads, 1) project_bwd_tc_kernel(const TcBwdArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    using ST = typename std::conditional<BF16, __nv_bfloat16, float>::type;
+    const int F = a.F, HC = a.HC, O = 2 * a.HC, OP = a.OP, N1 = a.N1, NP2 = a.NP2, nst = a.stages;
+    const bool need_dx = a.dx != nullptr;
+    const TcBwdSmem L = tc_bwd_smem<BF16>(F, HC, OP, N1, NP2, nst);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bars);
+    uint64_t *full = bars, *empty = bars + kBwdMaxStages;
+    uint64_t *ops_ready = bars + 2 * kBwdMaxStages, *ops_free = ops_ready + 1;
+    uint64_t *t_full = ops_ready + 2, *t_empty = ops_ready + 4;
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(smem + L.tmem_ptr);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t num_tiles = (a.R + kTileM - 1) / kTileM;
+    const int n_local = blockIdx.x < num_tiles ? (int)((num_tiles - 1 - blockIdx.x) / gridDim.x) + 1 : 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < kBwdMaxStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kBwdWorkers);
+        }
+        mbar_init(ops_ready, kBwdWorkers);
+        mbar_init(ops_free, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&t_full[i], 1);
+            mbar_init(&t_empty[i], kBwdWorkers);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr, a.tmem_cols);
+    // B operand of GEMM1: B1[n = f][k = o] = Wcat[o][f]  (K-major), zero padded
+    for (int n = tid; n < N1; n += kBwdThreads) {
+        write_row_canonical<BF16>(smem + L.w_hi, smem + L.w_lo, n, L.P_w, n < F ? O : 0, OP, [&](int o) {
+            return o < HC ? a.wl[(int64_t)o * F + n] : a.wr[(int64_t)(o - HC) * F + n];
+        });
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===== TMA producer: three contiguous bulk copies per tile (dxl, dxr, x) ==================================
+        if (lane == 0) {
+            int it = 0;
+            for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int s = it % nst;
+                if (it >= nst) mbar_wait(&empty[s], ((it / nst) - 1) & 1);
+                const int64_t r0 = tile * kTileM;
+                const int nr = (int)((a.R - r0) < (int64_t)kTileM ? (a.R - r0) : (int64_t)kTileM);
+                unsigned char *st = smem + L.stage0 + s * L.stage_bytes;
+                const uint32_t bd = (uint32_t)nr * HC * (uint32_t)sizeof(ST), bx = (uint32_t)nr * F * 4u;
+                const unsigned char *srcs[3] = {reinterpret_cast<const unsigned char *>(static_cast<const ST *>(a.dxl) + r0 * HC),
+                                                reinterpret_cast<const unsigned char *>(static_cast<const ST *>(a.dxr) + r0 * HC),
+                                                reinterpret_cast<const unsigned char *>(a.x + r0 * F)};
+                unsigned char *dsts[3] = {st, st + L.tile_d, st + 2 * L.tile_d};
+                const uint32_t lens[3] = {bd, bd, bx};
+                uint32_t tx = 0;
+                for (int q = 0; q < 3; ++q) {  // <16-byte ragged ends (last tile only): plain 2-byte copies
+                    const uint32_t mid = lens[q] & ~15u;
+                    for (uint32_t b = mid; b < lens[q]; b += 2)
+                        *reinterpret_cast<uint16_t *>(dsts[q] + b) = *reinterpret_cast<const uint16_t *>(srcs[q] + b);
+                    tx += mid;
+                }
+                mbar_arrive_expect_tx(&full[s], tx);
+                for (int q = 0; q < 3; ++q) {
+                    const uint32_t mid = lens[q] & ~15u;
+                    if (mid) bulk_g2s(dsts[q], srcs[q], mid, &full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer ==============================================================================================
+        const uint32_t fmt = BF16 ? kFmtBF16 : kFmtTF32;
+        const uint32_t idesc1 = umma_idesc(fmt, kTileM, N1, 0, 0);
+        const uint32_t idesc2 = umma_idesc(fmt, kTileM, NP2, 1, 1);
+        const uint32_t w_hi = smem_u32(smem + L.w_hi), w_lo = smem_u32(smem + L.w_lo);
+        const uint32_t d_hi = smem_u32(smem + L.d_hi), d_lo = smem_u32(smem + L.d_lo);
+        const uint32_t x_hi = smem_u32(smem + L.x_hi), x_lo = smem_u32(smem + L.x_lo);
+        const int ksteps1 = BF16 ? OP / 16 : OP / 8;         // K = gradient columns, 32 bytes per MMA
+        const int ksteps2 = BF16 ? kTileM / 16 : kTileM / 8;  // K = rows: 8 (tf32) / 16 (bf16) rows per MMA
+        const uint32_t kb = BF16 ? 2 : 1;                     // 8-row blocks per MMA
+        const uint32_t d2 = tmem_base + a.d2_col;
+        uint32_t acc2 = 0;
+        for (int it = 0; it < n_local; ++it) {
+            mbar_wait(ops_ready, it & 1);
+            if (need_dx && it >= 2) mbar_wait(&t_empty[it & 1], ((it >> 1) - 1) & 1);
+            tc_fence_after();
+            if (lane == 0) {
+                if (need_dx) {
+                    const uint32_t d1 = tmem_base + (uint32_t)(it & 1) * a.d1_stride;
+                    uint32_t acc = 0;
+                    for (int ks = 0; ks < ksteps1; ++ks) {
+                        const uint32_t ko = ks * 256;
+                        if (BF16) {
+                            umma_bf16(d1, umma_desc(d_hi + ko, 128, L.P_d), umma_desc(w_hi + ko, 128, L.P_w), idesc1, acc);
+                        } else {
+                            umma_tf32(d1, umma_desc(d_lo + ko, 128, L.P_d), umma_desc(w_hi + ko, 128, L.P_w), idesc1, acc);
+                            umma_tf32(d1, umma_desc(d_hi + ko, 128, L.P_d), umma_desc(w_lo + ko, 128, L.P_w), idesc1, 1);
+                            umma_tf32(d1, umma_desc(d_hi + ko, 128, L.P_d), umma_desc(w_hi + ko, 128, L.P_w), idesc1, 1);
+                        }
+                        acc = 1;
+                    }
+                    umma_commit(&t_full[it & 1]);
+                }
+                for (int ks = 0; ks < ksteps2; ++ks) {
+                    const uint32_t da = ks * kb * L.P_d, dbx = ks * kb * L.P_x;
+                    if (BF16) {
+                        umma_bf16(d2, umma_desc(d_hi + da, L.P_d, 128), umma_desc(x_hi + dbx, L.P_x, 128), idesc2, acc2);
+                    } else {
+                        umma_tf32(d2, umma_desc(d_lo + da, L.P_d, 128), umma_desc(x_hi + dbx, L.P_x, 128), idesc2, acc2);
+                        umma_tf32(d2, umma_desc(d_hi + da, L.P_d, 128), umma_desc(x_lo + dbx, L.P_x, 128), idesc2, 1);
+                        umma_tf32(d2, umma_desc(d_hi + da, L.P_d, 128), umma_desc(x_hi + dbx, L.P_x, 128), idesc2, 1);
+                    }
+                    acc2 = 1;
+                }
+                umma_commit(ops_free);  // both GEMMs have consumed the operand buffers
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===== workers ===================================================================================================
+        const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int row = quarter * 32 + lane;
+        const int wt = (warp - 2) * 32 + lane;  // 0..255
+        const bool issuer = (wt == 0);
+        float *dx_st = reinterpret_cast<float *>(smem + L.dx_st);
+        for (int it = 0; it <= n_local; ++it) {
+            if (it < n_local) {
+                const int s = it % nst;
+                const int64_t tile = blockIdx.x + (int64_t)it * gridDim.x;
+                const int64_t r0 = tile * kTileM;
+                const int nr = (int)((a.R - r0) < (int64_t)kTileM ? (a.R - r0) : (int64_t)kTileM);
+                mbar_wait(&full[s], (it / nst) & 1);
+                if (it >= 1) mbar_wait(ops_free, (it - 1) & 1);
+                const unsigned char *st = smem + L.stage0 + s * L.stage_bytes;
+                const bool live = row < nr;  // rows past the end of the last tile must contribute ZERO to GEMM2
+                if (half == 0) {
+                    const ST *gl = reinterpret_cast<const ST *>(st) + row * HC;
+                    const ST *gr = reinterpret_cast<const ST *>(st + L.tile_d) + row * HC;
+                    write_row_canonical<BF16>(smem + L.d_hi, smem + L.d_lo, row, L.P_d, live ? O : 0, OP,
+                                              [&](int o) { return o < HC ? ld_elem(gl + o) : ld_elem(gr + (o - HC)); });
+                } else {
+                    const float *xrow = reinterpret_cast<const float *>(st + 2 * L.tile_d) + row * F;
+                    write_row_canonical<BF16>(smem + L.x_hi, smem + L.x_lo, row, L.P_x, live ? F + 1 : 0, NP2,
+                                              [&](int f) { return f < F ? xrow[f] : 1.f; });
+                }
+                fence_proxy_async();
+                mbar_arrive(ops_ready);
+                mbar_arrive(&empty[s]);
+            }
+            if (need_dx && it >= 1) {
+                const int j = it - 1, acc = j & 1;
+                const int64_t tile = blockIdx.x + (int64_t)j * gridDim.x;
+                const int64_t r0 = tile * kTileM;
+                const int nr = (int)((a.R - r0) < (int64_t)kTileM ? (a.R - r0) : (int64_t)kTileM);
+                mbar_wait(&t_full[acc], (j >> 1) & 1);
+                tc_fence_after();
+                if (issuer) bulk_wait_read0();
+                named_bar_sync(1, kBwdWorkers);
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * a.d1_stride;
+                for (int cb = half; cb < N1 / 16; cb += 2) {
+                    float v[16];
+                    tmem_ld16(taddr + cb * 16, v);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int f = cb * 16 + i;
+                        if (f < F) dx_st[row * F + f] = v[i];
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&t_empty[acc]);
+                fence_proxy_async();
+                named_bar_sync(1, kBwdWorkers);
+                float *gdx = a.dx + r0 * F;
+                if (nr == kTileM) {
+                    if (issuer) {
+                        bulk_s2g(gdx, dx_st, kTileM * F * 4u);
+                        bulk_commit();
+                    }
+                } else {
+                    for (int i = wt; i < nr * F; i += kBwdWorkers) gdx[i] = dx_st[i];
+                }
+            }
+        }
+        // ---- parameter-gradient partials: D2[m = o][n = f | bias] ------------------------------------------------
+        if (n_local > 0) {
+            mbar_wait(ops_free, (n_local - 1) & 1);  // every MMA of this CTA has completed
+            tc_fence_after();
+            float *out = a.partials + (int64_t)blockIdx.x * (O * F + O);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a.d2_col;
+            for (int cb = half; cb < NP2 / 16; cb += 2) {
+                float v[16];
+                tmem_ld16(taddr + cb * 16, v);
+                if (row < O) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int n = cb * 16 + i;
+                        if (n < F) out[row * F + n] = v[i];
+                        else if (n == F) out[O * F + row] = v[i];
+                    }
+                }
+            }
+        }
+        if (issuer) bulk_wait0();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, a.tmem_cols);
+    }
+}
+
+template <bool BF16>
+static bool bwd_tc_config(TcBwdArgs &a) {
+    a.OP = BF16 ? ((2 * a.HC + 15) / 16) * 16 : ((2 * a.HC + 7) / 8) * 8;
+    a.N1 = ((a.F + 15) / 16) * 16;
+    a.NP2 = ((a.F + 1 + 15) / 16) * 16;
+    if (2 * a.HC > 128 || a.N1 > 256 || a.NP2 > 256) return false;
+    a.d1_stride = pow2_cols(a.N1);
+    a.d2_col = 2 * a.d1_stride;
+    a.tmem_cols = pow2_cols(a.d2_col + a.NP2);
+    if (a.tmem_cols > 512) return false;
+    for (a.stages = kBwdMaxStages; a.stages >= 1; --a.stages)
+        if (tc_bwd_smem<BF16>(a.F, a.HC, a.OP, a.N1, a.NP2, a.stages).total <= 220u * 1024u) return true;
+    return false;
+}
+
+bool project_bwd_tc_supported(int F, int HC, int dtype) {
+    TcBwdArgs a{};
+    a.F = F; a.HC = HC;
+    return dtype == TECGAT_BF16 ? bwd_tc_config<true>(a) : bwd_tc_config<false>(a);
+}
+
+static int bwd_tc_grid(int64_t R) {
+    const int64_t tiles = (R + kTileM - 1) / kTileM;
+    return (int)(tiles < 148 ? tiles : 148);
+}
+
+int64_t project_bwd_tc_workspace(int64_t R, int F, int HC) {
+    const int64_t tc = int64_t(bwd_tc_grid(R)) * (2 * HC * F + 2 * HC) * (int64_t)sizeof(float);
+    const int64_t ff = project_bwd_ffma_workspace(R, F, HC);
+    return tc > ff ? tc : ff;
+}
+
+template <bool BF16>
+static int launch_bwd_tc(TcBwdArgs &a, float *dwl, float *dbl, float *dwr, float *dbr, cudaStream_t st) {
+    bwd_tc_config<BF16>(a);
+    const TcBwdSmem L = tc_bwd_smem<BF16>(a.F, a.HC, a.OP, a.N1, a.NP2, a.stages);
+    auto kern = project_bwd_tc_kernel<BF16>;
+    TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    const int grid = bwd_tc_grid(a.R);
+    kern<<<grid, kBwdThreads, L.total, st>>>(a);
+    TG_LAUNCH_CHECK();
+    const int O = 2 * a.HC, F = a.F, HC = a.HC;
+    ReduceSegs segs = {{dwl, dwr, dbl, dbr}, {0, HC * F, O * F, O * F + HC}, {HC * F, O * F, O * F + HC, O * F + O}};
+    return reduce_columns(a.partials, grid, O * F + O, segs, st);
+}
+
 int project_bwd_tc(const void *dxl, const void *dxr, const float *x, const float *wl, const float *wr, float *dx,
                    float *dwl, float *dbl, float *dwr, float *dbr, void *workspace, int64_t R, int F, int HC, int dtype,
                    cudaStream_t st) {
-    return project_bwd_ffma(dxl, dxr, x, wl, wr, dx, dwl, dbl, dwr, dbr, workspace, R, F, HC, dtype, st);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dxl) | reinterpret_cast<uintptr_t>(dxr) |
+                           reinterpret_cast<uintptr_t>(dx)) & 15) == 0;
+    if (!aligned || !project_bwd_tc_supported(F, HC, dtype))  // shapes beyond the tensor-core kernel's shared-memory budget
+        return project_bwd_ffma(dxl, dxr, x, wl, wr, dx, dwl, dbl, dwr, dbr, workspace, R, F, HC, dtype, st);
+    TcBwdArgs a{};
+    a.dxl = dxl; a.dxr = dxr; a.x = x; a.wl = wl; a.wr = wr; a.dx = dx; a.partials = static_cast<float *>(workspace);
+    a.R = R; a.F = F; a.HC = HC;
+    return dtype == TECGAT_BF16 ? launch_bwd_tc<true>(a, dwl, dbl, dwr, dbr, st) : launch_bwd_tc<false>(a, dwl, dbl, dwr, dbr, st);
 }
 
 }  // namespace tg

@@ -134,6 +134,46 @@ def test_projection_forward(cuda_device, impl, R, F, HC):
     assert rel_err(xl16.float(), ref_l) <= 1e-2 and rel_err(xr16.float(), ref_r) <= 1e-2
 
 
+@pytest.mark.parametrize("impl", ["ffma", "tc"])
+@pytest.mark.parametrize("R,F,HC,need_dx", [(1000, 22, 22, True), (128 * 700 + 13, 22, 22, True), (77, 10, 10, True),
+                                            (128 * 40, 22, 22, False), (300, 7, 6, True), (128 * 3 + 1, 22, 44, True)])
+def test_projection_backward(cuda_device, impl, R, F, HC, need_dx):
+    """dx = dxl Wl + dxr Wr, dW = d^T x, db = sum d: tensor-core (3xTF32, TMEM-accumulated dW) and CUDA-core kernels vs
+    fp64 matmul; many tiles per CTA, ragged last tile, dx skipped when the input needs no gradient."""
+    from tec_mollm_b200 import _lib
+
+    gen = torch.Generator().manual_seed(R * 7 + F)
+    x = torch.randn(R, F, generator=gen)
+    dxl, dxr = torch.randn(R, HC, generator=gen), torch.randn(R, HC, generator=gen)
+    wl, wr = torch.randn(HC, F, generator=gen) * 0.3, torch.randn(HC, F, generator=gen) * 0.3
+    code = _lib.PROJ_TC if impl == "tc" else _lib.PROJ_FFMA
+    p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+    ref_dx = dxl.double() @ wl.double() + dxr.double() @ wr.double()
+    refs = {"dwl": dxl.double().t() @ x.double(), "dwr": dxr.double().t() @ x.double(),
+            "dbl": dxl.double().sum(0), "dbr": dxr.double().sum(0)}
+    for dtype, st, tol in ((_lib.F32, torch.float32, 3e-6), (_lib.BF16, torch.bfloat16, 1e-2)):
+        d = lambda t: t.to(cuda_device)
+        xd, wld, wrd = d(x), d(wl), d(wr)
+        dl, dr = d(dxl).to(st), d(dxr).to(st)
+        dx = torch.full((R, F), float("nan"), device=cuda_device) if need_dx else None
+        outs = {k: torch.full(v.shape, float("nan"), device=cuda_device) for k, v in refs.items()}
+        ws = torch.empty(max(1, _lib.lib().tecgat_project_bwd_workspace(R, F, HC, code)), dtype=torch.uint8, device=cuda_device)
+        _lib.call("tecgat_project_bwd", p(dl), p(dr), p(xd), p(wld), p(wrd), p(dx), p(outs["dwl"]), p(outs["dbl"]),
+                  p(outs["dwr"]), p(outs["dbr"]), p(ws), R, F, HC, dtype, code,
+                  C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        if dtype == _lib.BF16:  # the bf16 contract rounds the operands first: compare against the rounded operands
+            dl64, dr64 = dl.double().cpu(), dr.double().cpu()
+            r_dx = dl64 @ wl.double() + dr64 @ wr.double()
+            r = {"dwl": dl64.t() @ x.double(), "dwr": dr64.t() @ x.double(), "dbl": dl64.sum(0), "dbr": dr64.sum(0)}
+        else:
+            r_dx, r = ref_dx, refs
+        if need_dx:
+            assert rel_err(dx, r_dx) <= tol, f"dx {rel_err(dx, r_dx):.3e}"
+        for k in r:
+            assert rel_err(outs[k], r[k]) <= tol, f"{k} {rel_err(outs[k], r[k]):.3e} (dtype {dtype})"
+
+
 # ---------------------------------------------------------------------------------------------------------
 # fused path vs oracle
 # ---------------------------------------------------------------------------------------------------------
