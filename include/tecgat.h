@@ -86,8 +86,8 @@ int tecgat_project_bwd(const void *dxl_dev, const void *dxr_dev, const float *x_
 
 /* ---- fused edge phase: replaces gather + LeakyReLU*att + segment softmax + dropout + scatter-add
  *      + bias (~20 ATen launches in PyG) with one kernel over all snapshots.
- *      dropout_p == 0 disables dropout; otherwise keep-mask bit for (snapshot s, CSR slot k, head h)
- *      is tecgat_dropout_keep(seed, s*E + k, h, p) (see tecgat_dropout_mask_host).                */
+ *      dropout_p == 0 disables dropout; otherwise the keep bit of (snapshot s, CSR slot k, head h) is the
+ *      counter-based hash restated by tecgat_dropout_mask_host.  negative_slope must lie in [0, 1].   */
 int tecgat_edge_fwd(const tecgat_plan_t *plan, const void *xl_dev, const void *xr_dev,
                     const float *att_dev, const float *bias_dev, float *y_dev, float *m_dev,
                     float *den_dev, int32_t snapshots, int32_t heads, int32_t out_channels,
@@ -105,9 +105,10 @@ int tecgat_edge_bwd(const tecgat_plan_t *plan, const void *xl_dev, const void *x
                     float dropout_p, uint64_t seed, int32_t mode, int32_t dtype, void *stream);
 
 /* Host restatement of the kernels' counter-based dropout RNG (pure integer arithmetic), so tests can
- * hand the oracle exactly the mask the kernels used.  keep_host: (count, heads) bytes, slot-major.  */
+ * hand the oracle exactly the mask the kernels used.  Global slot g = snapshot * edges_per_snapshot + CSR slot;
+ * keep_host: (count, heads) bytes for g = first_slot .. first_slot + count - 1.                      */
 int tecgat_dropout_mask_host(uint64_t seed, int64_t first_slot, int64_t count, int32_t heads,
-                             float dropout_p, uint8_t *keep_host);
+                             float dropout_p, int64_t edges_per_snapshot, uint8_t *keep_host);
 
 /* ---- graph builder: replaces calculate_haversine_distance_matrix (src/graph/graph_constructor.py:34-59,
  *      sklearn haversine_distances in fp64), construct_binary_adjacency (:61-81, inclusive `<=`, zero

@@ -172,27 +172,30 @@ __device__ __forceinline__ float ld_elem(const __nv_bfloat16 *p) { return __bflo
 __device__ __forceinline__ void st_elem(float *p, float v) { *p = v; }
 __device__ __forceinline__ void st_elem(__nv_bfloat16 *p, float v) { *p = __float2bfloat16_rn(v); }
 
-// ---- counter-based dropout RNG: integer-only, restated on the host in api.cu -----------------
-// keep(seed, slot, head) with slot = snapshot * E + csr_slot.  32-bit multiply/xorshift mixing
-// (murmur3 fmix32 over the two counter words and the two seed words): ~10 integer instructions per
-// draw; the top 24 bits give a uniform in [0, 1).
-__host__ __device__ __forceinline__ uint32_t dropout_bits(uint64_t seed, uint64_t slot, uint32_t head,
-                                                          uint32_t heads) {
-    const uint64_t ctr = slot * heads + head;
-    uint32_t h = (static_cast<uint32_t>(ctr) ^ static_cast<uint32_t>(seed)) * 0x9E3779B1u;
-    h ^= (static_cast<uint32_t>(ctr >> 32) + static_cast<uint32_t>(seed >> 32)) * 0x85EBCA77u + 0x27D4EB2Fu;
+// ---- counter-based dropout RNG: integer-only, restated on the host (tecgat_dropout_mask_host) -----------------
+// keep(seed, snapshot, CSR slot, head).  The 64-bit seed and the snapshot index are folded ONCE per CTA into a 32-bit
+// per-snapshot key; per (slot, head pair) one murmur3-style 32-bit finaliser (3 multiplies, 3 xor-shifts) yields two
+// 16-bit uniforms, one per head of the pair.  P(drop) = round(p * 65536) / 65536.
+__host__ __device__ __forceinline__ uint32_t fmix32(uint32_t h) {
     h ^= h >> 16;
     h *= 0x85EBCA6Bu;
     h ^= h >> 13;
     h *= 0xC2B2AE35u;
     h ^= h >> 16;
-    return h >> 8;  // 24 bits
+    return h;
+}
+__host__ __device__ __forceinline__ uint32_t dropout_snapshot_key(uint64_t seed, uint32_t snapshot) {
+    return fmix32(static_cast<uint32_t>(seed) ^ fmix32(static_cast<uint32_t>(seed >> 32) + 0x9E3779B9u * (snapshot + 1u)));
+}
+__host__ __device__ __forceinline__ uint32_t dropout_bits16(uint32_t key, uint32_t slot, uint32_t head) {
+    const uint32_t h = fmix32((slot * 0x9E3779B1u) ^ key ^ ((head >> 1) * 0x7FEB352Du));
+    return (h >> ((head & 1u) * 16u)) & 0xFFFFu;
 }
 __host__ __device__ __forceinline__ uint32_t dropout_threshold(float p) {
-    // keep iff bits >= thr;  P(drop) = thr / 2^24
-    double t = static_cast<double>(p) * 16777216.0;
+    // keep iff bits16 >= thr;  P(drop) = thr / 65536
+    double t = static_cast<double>(p) * 65536.0;
     if (t < 0) t = 0;
-    if (t > 16777216.0) t = 16777216.0;
+    if (t > 65536.0) t = 65536.0;
     return static_cast<uint32_t>(t + 0.5);
 }
 

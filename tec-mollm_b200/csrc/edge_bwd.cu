@@ -107,28 +107,23 @@ __device__ __forceinline__ void edge_bwd_body(const EdgeBwdArgs &a, unsigned cha
         __syncthreads();
     }
 
+    constexpr int CP = (C + 1) / 2;
+    constexpr float kLog2e = 1.4426950408889634f;
     const int node_l = tid / H;
     const int h = tid - node_l * H;
     const bool active = node_l < nt;
-    float dxl[C], dxr[C], datt[C];
+    float2 dxl[CP], dxr[CP], datt[CP];
 #pragma unroll
-    for (int c = 0; c < C; ++c) dxl[c] = dxr[c] = datt[c] = 0.f;
+    for (int i = 0; i < CP; ++i) dxl[i] = dxr[i] = datt[i] = make_float2(0.f, 0.f);
 
     if (active) {
         const int v = n0 + node_l;
         const int vl = v - lo;
-        float xl_v[C], xr_v[C], g_v[C], att_h[C];
-        {
-            const ST *pl = xl_w + vl * HC + h * C, *pr = xr_w + vl * HC + h * C;
-            const float *pg = g_w + vl * HC + h * C;
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                xl_v[c] = ld_elem(pl + c);
-                xr_v[c] = ld_elem(pr + c);
-                g_v[c] = pg[c];
-                att_h[c] = __ldg(a.att + h * C + c);
-            }
-        }
+        float2 xl_v[CP], xr_v[CP], g_v[CP], att_h[CP];
+        load_row<C>(xl_w + vl * HC + h * C, xl_v);
+        load_row<C>(xr_w + vl * HC + h * C, xr_v);
+        load_row<C>(g_w + vl * HC + h * C, g_v);
+        load_row<C>(a.att + h * C, att_h);
         float m_v, inv_v, delta_v;
         if (SM) {
             m_v = m_s[vl * H + h];
@@ -137,85 +132,89 @@ __device__ __forceinline__ void edge_bwd_body(const EdgeBwdArgs &a, unsigned cha
         } else {
             m_v = m_g[vl * H + h];
             inv_v = 1.f / den_g[vl * H + h];
-            const float *yp = y_g + vl * HC + h * C;
-            delta_v = 0.f;
+            float2 yv[CP], bh[CP], d2 = make_float2(0.f, 0.f);
+            load_row<C>(y_g + vl * HC + h * C, yv);
+            load_row<C>(a.bias + h * C, bh);
 #pragma unroll
-            for (int c = 0; c < C; ++c) delta_v = fmaf(g_v[c], yp[c] - __ldg(a.bias + h * C + c), delta_v);
+            for (int i = 0; i < CP; ++i) d2 = __ffma2_rn(g_v[i], __fadd2_rn(yv[i], make_float2(-bh[i].x, -bh[i].y)), d2);
+            delta_v = hsum(d2);
         }
-        const uint64_t slot0 = static_cast<uint64_t>(snap) * static_cast<uint64_t>(a.E);
+        const uint32_t key = a.drop_thr ? dropout_snapshot_key(a.seed, (uint32_t)snap) : 0u;
+        const float2 slope2 = make_float2(a.slope, a.slope);
+        const float dslope = 1.f - a.slope;  // lrelu'(s) = slope + (1 - slope) * [s > 0]
+        const float2 dslope2 = make_float2(dslope, dslope);
 
-        // ---- role 1: v as DESTINATION, in-edges (u -> v) ----------------------------------------------
+        // ---- role 1: v as DESTINATION, in-edges (u -> v): d xr_v, d att ---------------------------------------
         {
             const int k1 = __ldg(a.rowptr_in + v + 1);
             const int k0 = self_only ? k1 - 1 : __ldg(a.rowptr_in + v);
+            const ST *base = xl_w + h * C;
             for (int k = k0; k < k1; ++k) {
                 const int u = __ldg(a.col_in + k) - lo;
-                const ST *p = xl_w + static_cast<int64_t>(u) * HC + h * C;
-                float t[C], z[C];
-                float e = 0.f, gx = 0.f;
+                float2 xu[CP], s[CP], z[CP];
+                load_row<C>(base + u * HC, xu);
+                const float e = edge_score<C, ST>(att_h, xu, xr_v, slope2, s, z);
+                float2 gx2 = make_float2(0.f, 0.f);
 #pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    const float xu = ld_elem(p + c);
-                    t[c] = Round<ST>::r(xu + xr_v[c]);
-                    z[c] = Round<ST>::r(leaky(t[c], a.slope));
-                    e = fmaf(att_h[c], z[c], e);
-                    gx = fmaf(g_v[c], xu, gx);
-                }
+                for (int i = 0; i < CP; ++i) gx2 = __ffma2_rn(g_v[i], xu[i], gx2);
                 float q = 1.f;
-                if (a.drop_thr) q = dropout_bits(a.seed, slot0 + (uint32_t)k, (uint32_t)h, (uint32_t)H) >= a.drop_thr ? a.inv_keep : 0.f;
-                const float alpha = __expf(e - m_v) * inv_v;
-                const float de = alpha * (q * gx - delta_v);
+                if (a.drop_thr) q = dropout_bits16(key, (uint32_t)k, (uint32_t)h) >= a.drop_thr ? a.inv_keep : 0.f;
+                const float alpha = fast_exp2(fmaf(e, kLog2e, -m_v)) * inv_v;
+                const float de = alpha * fmaf(q, hsum(gx2), -delta_v);
+                const float2 de2 = make_float2(de, de);
 #pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    datt[c] = fmaf(de, z[c], datt[c]);
-                    const float dea = de * att_h[c];
-                    dxr[c] += t[c] > 0.f ? dea : dea * a.slope;
+                for (int i = 0; i < CP; ++i) {
+                    datt[i] = __ffma2_rn(de2, z[i], datt[i]);
+                    const float2 step = make_float2(s[i].x > 0.f ? 1.f : 0.f, s[i].y > 0.f ? 1.f : 0.f);
+                    const float2 d = __ffma2_rn(step, dslope2, slope2);
+                    dxr[i] = __ffma2_rn(__fmul2_rn(de2, att_h[i]), d, dxr[i]);
                 }
             }
         }
-        // ---- role 2: v as SOURCE, out-edges (v -> u) ---------------------------------------------------
+        // ---- role 2: v as SOURCE, out-edges (v -> u): d xl_v ---------------------------------------------------
         {
             const int k1 = __ldg(a.rowptr_out + v + 1);
             const int k0 = self_only ? k1 - 1 : __ldg(a.rowptr_out + v);
+            const ST *base_r = xr_w + h * C;
+            const float *base_g = g_w + h * C;
             for (int k2 = k0; k2 < k1; ++k2) {
                 const int u = __ldg(a.col_out + k2) - lo;
-                const ST *pr = xr_w + static_cast<int64_t>(u) * HC + h * C;
-                const float *pg = g_w + static_cast<int64_t>(u) * HC + h * C;
-                float t[C], gu[C];
-                float e = 0.f, gx = 0.f;
+                float2 xru[CP], gu[CP], s[CP], z[CP];
+                load_row<C>(base_r + u * HC, xru);
+                load_row<C>(base_g + u * HC, gu);
+                const float e = edge_score<C, ST>(att_h, xl_v, xru, slope2, s, z);
+                float2 gx2 = make_float2(0.f, 0.f);
 #pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    gu[c] = pg[c];
-                    t[c] = Round<ST>::r(xl_v[c] + ld_elem(pr + c));
-                    const float z = Round<ST>::r(leaky(t[c], a.slope));
-                    e = fmaf(att_h[c], z, e);
-                    gx = fmaf(gu[c], xl_v[c], gx);
-                }
+                for (int i = 0; i < CP; ++i) gx2 = __ffma2_rn(gu[i], xl_v[i], gx2);
                 float m_u, inv_u, delta_u;
                 if (SM) {
                     m_u = m_s[u * H + h];
                     inv_u = inv_s[u * H + h];
                     delta_u = delta_s[u * H + h];
                 } else {
-                    m_u = m_g[static_cast<int64_t>(u) * H + h];
-                    inv_u = 1.f / den_g[static_cast<int64_t>(u) * H + h];
-                    const float *yp = y_g + static_cast<int64_t>(u) * HC + h * C;
-                    delta_u = 0.f;
+                    m_u = m_g[u * H + h];
+                    inv_u = 1.f / den_g[u * H + h];
+                    float2 yu[CP], bh[CP], d2 = make_float2(0.f, 0.f);
+                    load_row<C>(y_g + u * HC + h * C, yu);
+                    load_row<C>(a.bias + h * C, bh);
 #pragma unroll
-                    for (int c = 0; c < C; ++c) delta_u = fmaf(gu[c], yp[c] - __ldg(a.bias + h * C + c), delta_u);
+                    for (int i = 0; i < CP; ++i) d2 = __ffma2_rn(gu[i], __fadd2_rn(yu[i], make_float2(-bh[i].x, -bh[i].y)), d2);
+                    delta_u = hsum(d2);
                 }
                 float q = 1.f;
                 if (a.drop_thr) {
                     const uint32_t kin = (uint32_t)__ldg(a.slot_out + k2);
-                    q = dropout_bits(a.seed, slot0 + kin, (uint32_t)h, (uint32_t)H) >= a.drop_thr ? a.inv_keep : 0.f;
+                    q = dropout_bits16(key, kin, (uint32_t)h) >= a.drop_thr ? a.inv_keep : 0.f;
                 }
-                const float alpha = __expf(e - m_u) * inv_u;
+                const float alpha = fast_exp2(fmaf(e, kLog2e, -m_u)) * inv_u;
                 const float aq = alpha * q;
-                const float de = alpha * (q * gx - delta_u);
+                const float de = alpha * fmaf(q, hsum(gx2), -delta_u);
+                const float2 aq2 = make_float2(aq, aq), de2 = make_float2(de, de);
 #pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    const float dea = de * att_h[c];
-                    dxl[c] = fmaf(aq, gu[c], dxl[c]) + (t[c] > 0.f ? dea : dea * a.slope);
+                for (int i = 0; i < CP; ++i) {
+                    const float2 step = make_float2(s[i].x > 0.f ? 1.f : 0.f, s[i].y > 0.f ? 1.f : 0.f);
+                    const float2 d = __ffma2_rn(step, dslope2, slope2);
+                    dxl[i] = __ffma2_rn(__fmul2_rn(de2, att_h[i]), d, __ffma2_rn(aq2, gu[i], dxl[i]));
                 }
             }
         }
@@ -233,12 +232,10 @@ __device__ __forceinline__ void edge_bwd_body(const EdgeBwdArgs &a, unsigned cha
     float *red = reinterpret_cast<float *>(y_base);  // (C, nt*H) d att scratch
     const int ntl = nt * H;
     if (active) {
+        store_row<C>(dxl_s + node_l * HC + h * C, dxl);
+        store_row<C>(dxr_s + node_l * HC + h * C, dxr);
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-            st_elem(dxl_s + node_l * HC + h * C + c, dxl[c]);
-            st_elem(dxr_s + node_l * HC + h * C + c, dxr[c]);
-            red[c * ntl + tid] = datt[c];
-        }
+        for (int c = 0; c < C; ++c) red[c * ntl + tid] = (c & 1) ? datt[c / 2].y : datt[c / 2].x;
     }
     __syncthreads();
     ST *dxl_g = static_cast<ST *>(a.dxl) + (static_cast<int64_t>(snap) * a.N + n0) * HC;
@@ -266,7 +263,7 @@ __device__ __forceinline__ void edge_bwd_body(const EdgeBwdArgs &a, unsigned cha
 }
 
 template <int C, typename ST>
-__global__ void __launch_bounds__(256) edge_bwd_kernel(const EdgeBwdArgs a) {
+__global__ void __launch_bounds__(256, 2) edge_bwd_kernel(const EdgeBwdArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tile = blockIdx.x % a.num_tiles;
     const int snap = blockIdx.x / a.num_tiles;
@@ -320,6 +317,7 @@ extern "C" int tecgat_edge_bwd(const tecgat_plan_t *plan, const void *xl, const 
                TECGAT_EINVAL, "edge_bwd: NULL argument");
     TG_REQUIRE(snapshots > 0 && heads > 0 && out_channels > 0, TECGAT_EINVAL, "edge_bwd: non-positive size");
     TG_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, TECGAT_EINVAL, "edge_bwd: dropout_p %f outside [0, 1)", dropout_p);
+    TG_REQUIRE(negative_slope >= 0.f && negative_slope <= 1.f, TECGAT_ENOSUP, "edge_bwd: negative_slope %f outside [0, 1]", negative_slope);
     TG_REQUIRE(mode == TECGAT_MODE_SHARED || mode == TECGAT_MODE_LITERAL, TECGAT_EINVAL, "edge_bwd: bad mode %d", mode);
     TG_REQUIRE(dtype == TECGAT_F32 || dtype == TECGAT_BF16, TECGAT_EINVAL, "edge_bwd: bad dtype %d", dtype);
     const int threads = ((plan->tile_nodes * heads + 31) / 32) * 32;

@@ -21,9 +21,9 @@ struct EdgeFwdArgs {
     int32_t win_rows_smem;  // rows of the xl window that fit in the shared-memory slab
 };
 
-template <int C, typename ST>
-__global__ void __launch_bounds__(256) edge_fwd_kernel(const EdgeFwdArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+template <int C, typename ST, bool SM>
+__device__ __forceinline__ void edge_fwd_body(const EdgeFwdArgs &a, unsigned char *smem_raw) {
+    constexpr int CP = (C + 1) / 2;
     const int tid = threadIdx.x;
     const int tile = blockIdx.x % a.num_tiles;
     const int snap = blockIdx.x / a.num_tiles;
@@ -35,7 +35,6 @@ __global__ void __launch_bounds__(256) edge_fwd_kernel(const EdgeFwdArgs a) {
     int lo = a.tile_lo[tile], hi = a.tile_hi[tile];
     if (self_only) { lo = n0; hi = n1; }
     const int win = hi - lo;
-    const bool use_smem = win <= a.win_rows_smem;
 
     const ST *xl_g = static_cast<const ST *>(a.xl) + (static_cast<int64_t>(snap) * a.N + lo) * HC;
     const ST *xr_g = static_cast<const ST *>(a.xr) + (static_cast<int64_t>(snap) * a.N + n0) * HC;
@@ -47,7 +46,7 @@ __global__ void __launch_bounds__(256) edge_fwd_kernel(const EdgeFwdArgs a) {
     unsigned char *xl_base = reinterpret_cast<unsigned char *>(y_s) + round16(a.T * HC * sizeof(float));
 
     const CopyPlan cr = plan_copy(xr_g, xr_base, nt * HC * (uint32_t)sizeof(ST));
-    const CopyPlan cl = plan_copy(xl_g, xl_base, use_smem ? win * HC * (uint32_t)sizeof(ST) : 0u);
+    const CopyPlan cl = plan_copy(xl_g, xl_base, SM ? win * HC * (uint32_t)sizeof(ST) : 0u);
     if (tid == 0) {
         mbar_init(bar, 1);
         fence_mbar_init();
@@ -67,55 +66,63 @@ __global__ void __launch_bounds__(256) edge_fwd_kernel(const EdgeFwdArgs a) {
     const int h = tid - node_l * H;
     if (node_l < nt) {
         const int d = n0 + node_l;
-        const ST *xr_p = reinterpret_cast<const ST *>(cr.s) + node_l * HC + h * C;
-        float xr_i[C], att_h[C], acc[C];
+        float2 xr_i[CP], att_h[CP], acc[CP];
+        load_row<C>(reinterpret_cast<const ST *>(cr.s) + node_l * HC + h * C, xr_i);
+        load_row<C>(a.att + h * C, att_h);
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-            xr_i[c] = ld_elem(xr_p + c);
-            att_h[c] = __ldg(a.att + h * C + c);
-            acc[c] = 0.f;
-        }
-        int k1 = __ldg(a.rowptr + d + 1);
-        int k0 = self_only ? k1 - 1 : __ldg(a.rowptr + d);  // the self loop is the row's last slot
-        const ST *src_base = (use_smem ? reinterpret_cast<const ST *>(cl.s) : xl_g) + h * C;
-        const uint64_t slot0 = static_cast<uint64_t>(snap) * static_cast<uint64_t>(a.E);
-        float mx = -INFINITY, l = 0.f;
+        for (int i = 0; i < CP; ++i) acc[i] = make_float2(0.f, 0.f);
+        const int k1 = __ldg(a.rowptr + d + 1);
+        const int k0 = self_only ? k1 - 1 : __ldg(a.rowptr + d);  // the self loop is the row's last slot
+        // neighbour rows: shared window (SM) or global/L2 gather (window too large for shared memory)
+        const ST *src_base = (SM ? reinterpret_cast<const ST *>(cl.s) : xl_g) + h * C;
+        const uint32_t key = a.drop_thr ? dropout_snapshot_key(a.seed, (uint32_t)snap) : 0u;
+        const float2 slope2 = make_float2(a.slope, a.slope);
+        constexpr float kLog2e = 1.4426950408889634f;
+        float mx = -INFINITY, l = 0.f;  // running max (log2 domain) and running sum
         for (int k = k0; k < k1; ++k) {
             const int j = __ldg(a.col + k) - lo;
-            const ST *p = src_base + static_cast<int64_t>(j) * HC;
-            float xj[C];
-#pragma unroll
-            for (int c = 0; c < C; ++c) xj[c] = ld_elem(p + c);
-            float e = 0.f;
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                const float s = Round<ST>::r(xj[c] + xr_i[c]);
-                const float z = Round<ST>::r(leaky(s, a.slope));
-                e = fmaf(att_h[c], z, e);
-            }
+            float2 xj[CP], s[CP], z[CP];
+            load_row<C>(src_base + j * HC, xj);
+            const float e = edge_score<C, ST>(att_h, xj, xr_i, slope2, s, z) * kLog2e;
             float q = 1.f;
-            if (a.drop_thr) q = dropout_bits(a.seed, slot0 + (uint32_t)k, (uint32_t)h, (uint32_t)H) >= a.drop_thr ? a.inv_keep : 0.f;
+            if (a.drop_thr) q = dropout_bits16(key, (uint32_t)k, (uint32_t)h) >= a.drop_thr ? a.inv_keep : 0.f;
             const float mn = fmaxf(mx, e);
-            const float sc = __expf(mx - mn);
-            const float pe = __expf(e - mn);
+            const float sc = fast_exp2(mx - mn);
+            const float pe = fast_exp2(e - mn);
             l = fmaf(l, sc, pe);
-            const float w = pe * q;
+            const float2 sc2 = make_float2(sc, sc), w2 = make_float2(pe * q, pe * q);
 #pragma unroll
-            for (int c = 0; c < C; ++c) acc[c] = fmaf(acc[c], sc, w * xj[c]);
+            for (int i = 0; i < CP; ++i) acc[i] = __ffma2_rn(acc[i], sc2, __fmul2_rn(w2, xj[i]));
             mx = mn;
         }
         const float den = l + 1e-16f;
         const float inv = 1.f / den;
-        float *yo = y_s + node_l * HC + h * C;
+        float2 bias_h[CP], out[CP];
+        load_row<C>(a.bias + h * C, bias_h);
+        const float2 inv2 = make_float2(inv, inv);
 #pragma unroll
-        for (int c = 0; c < C; ++c) yo[c] = fmaf(acc[c], inv, __ldg(a.bias + h * C + c));
+        for (int i = 0; i < CP; ++i) out[i] = __ffma2_rn(acc[i], inv2, bias_h[i]);
+        store_row<C>(y_s + node_l * HC + h * C, out);
         const int64_t r = (static_cast<int64_t>(snap) * a.N + d) * H + h;
-        a.m[r] = mx;
+        a.m[r] = mx;   // softmax shift in the log2 domain (m * log2 e); consumed only by edge_bwd
         a.den[r] = den;
     }
     __syncthreads();
     float *y_g = a.y + (static_cast<int64_t>(snap) * a.N + n0) * HC;
     for (int i = tid; i < nt * HC; i += blockDim.x) y_g[i] = y_s[i];
+}
+
+template <int C, typename ST>
+__global__ void __launch_bounds__(256) edge_fwd_kernel(const EdgeFwdArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tile = blockIdx.x % a.num_tiles;
+    const int snap = blockIdx.x / a.num_tiles;
+    int win = a.tile_hi[tile] - a.tile_lo[tile];
+    if (a.literal && snap > 0) win = min(a.N, (tile + 1) * a.T) - tile * a.T;
+    if (win <= a.win_rows_smem)
+        edge_fwd_body<C, ST, true>(a, smem_raw);
+    else
+        edge_fwd_body<C, ST, false>(a, smem_raw);
 }
 
 template <int C, typename ST>
@@ -145,6 +152,7 @@ extern "C" int tecgat_edge_fwd(const tecgat_plan_t *plan, const void *xl, const 
     TG_REQUIRE(plan && xl && xr && att && bias && y && m && den, TECGAT_EINVAL, "edge_fwd: NULL argument");
     TG_REQUIRE(snapshots > 0 && heads > 0 && out_channels > 0, TECGAT_EINVAL, "edge_fwd: non-positive size");
     TG_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, TECGAT_EINVAL, "edge_fwd: dropout_p %f outside [0, 1)", dropout_p);
+    TG_REQUIRE(negative_slope >= 0.f && negative_slope <= 1.f, TECGAT_ENOSUP, "edge_fwd: negative_slope %f outside [0, 1]", negative_slope);
     TG_REQUIRE(mode == TECGAT_MODE_SHARED || mode == TECGAT_MODE_LITERAL, TECGAT_EINVAL, "edge_fwd: bad mode %d", mode);
     TG_REQUIRE(dtype == TECGAT_F32 || dtype == TECGAT_BF16, TECGAT_EINVAL, "edge_fwd: bad dtype %d", dtype);
     const int threads = ((plan->tile_nodes * heads + 31) / 32) * 32;

@@ -212,11 +212,15 @@ extern "C" int tecgat_plan_export(const tecgat_plan_t *p, int32_t *rowptr, int32
 }
 
 extern "C" int tecgat_dropout_mask_host(uint64_t seed, int64_t first_slot, int64_t count, int32_t heads,
-                                        float dropout_p, uint8_t *keep) {
-    TG_REQUIRE(keep && heads > 0 && count >= 0, TECGAT_EINVAL, "dropout_mask_host: bad argument");
+                                        float dropout_p, int64_t edges_per_snapshot, uint8_t *keep) {
+    // slot = snapshot * edges_per_snapshot + CSR slot (the kernels' numbering)
+    TG_REQUIRE(keep && heads > 0 && count >= 0 && edges_per_snapshot > 0, TECGAT_EINVAL, "dropout_mask_host: bad argument");
     const uint32_t thr = tg::dropout_threshold(dropout_p);
-    for (int64_t i = 0; i < count; ++i)
-        for (int32_t h = 0; h < heads; ++h)
-            keep[i * heads + h] = tg::dropout_bits(seed, uint64_t(first_slot + i), uint32_t(h), uint32_t(heads)) >= thr;
+    for (int64_t i = 0; i < count; ++i) {
+        const int64_t g = first_slot + i;
+        const uint32_t key = tg::dropout_snapshot_key(seed, uint32_t(g / edges_per_snapshot));
+        const uint32_t slot = uint32_t(g % edges_per_snapshot);
+        for (int32_t h = 0; h < heads; ++h) keep[i * heads + h] = tg::dropout_bits16(key, slot, uint32_t(h)) >= thr;
+    }
     return TECGAT_OK;
 }

@@ -322,7 +322,13 @@ int project_fwd_tc(const float *x, const float *wl, const float *bl, const float
 // read twice by the tensor core: as the K-major A operand of GEMM1 and as the MN-major A operand of GEMM2 -- no
 // transposition pass.  The x tile gets a constant-one column, so the bias gradients fall out of GEMM2 for free.
 // GEMM2 accumulates in TMEM across all the CTA's tiles; per-CTA partials + the fixed-order fp64 second stage
-// (reduce.cu) keep the parameter gradients deterministic.  fp32 contract: 3xTF32 on both GEMMs.
+// (reduce.cu) keep the parameter gradients deterministic.
+//
+// Precision.  tcgen05 returns zeros for MN-major kind::tf32 operands in the no-swizzle layout (measured with
+// tools/umma_probe.cu; kind::f16 MN-major works), so the fp32 contract cannot reuse the forward's 3xTF32 here.  Instead
+// every fp32 value is split into THREE bf16 terms, v = b0 + b1 + b2 (exact to 2^-27), and each GEMM issues the six
+// products of order <= 2 (b0b0, b0b1, b1b0, b1b1, b0b2, b2b0): error ~2^-26 per product, fp32 accumulation in TMEM --
+// tighter than 3xTF32, same MMA count (K = 16 per instruction instead of 8).  bf16 contract: one product.
 // CTA = 10 warps, one per SM: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-9 = workers (two threads per row: one
 // re-lays the gradient row, the other the x row; they split the epilogue columns).
 // =====================================================================================================================
@@ -337,32 +343,31 @@ struct TcBwdArgs {
     float *partials;  // (grid, 2*HC*F + 2*HC): [dWl | dWr | dbl | dbr] per CTA
     int64_t R;
     int32_t F, HC;
-    int32_t OP;   // 2*HC padded to the MMA K granularity (8 tf32 / 16 bf16)
+    int32_t OP;   // 2*HC padded to 16 (K of GEMM1)
     int32_t N1;   // F padded to 16 (GEMM1 N)
     int32_t NP2;  // F + 1 padded to 16 (GEMM2 N)
     int32_t d1_stride, d2_col, tmem_cols, stages;
 };
 
 struct TcBwdSmem {
-    uint32_t bars, tmem_ptr, w_hi, w_lo, d_hi, d_lo, x_hi, x_lo, stage0, dx_st, total;
-    uint32_t P_w, P_d, P_x, tile_d, tile_x, stage_bytes;
+    uint32_t bars, tmem_ptr, w, d, x, stage0, dx_st, total;  // w/d/x: first split; split q lives at + q * {w,d,x}_bytes
+    uint32_t P_w, P_d, P_x, w_bytes, d_bytes, x_bytes, tile_d, tile_x, stage_bytes;
 };
 
-template <bool BF16>
+// SPLIT = 1: bf16 contract (gradients already bf16);  SPLIT = 3: fp32 contract through the three-term bf16 split
+template <int SPLIT>
 __host__ __device__ inline TcBwdSmem tc_bwd_smem(int F, int HC, int OP, int N1, int NP2, int stages) {
-    const uint32_t elem = BF16 ? 2 : 4, epc = 16 / elem;
+    const uint32_t esz = SPLIT == 1 ? 2 : 4;  // bytes of a dxl / dxr element in global memory
     TcBwdSmem s;
     uint32_t o = 0;
     s.bars = o; o += 256;
     s.tmem_ptr = o; o += 128;
-    s.P_w = (OP / epc) * 128; s.P_d = (OP / epc) * 128; s.P_x = (NP2 / epc) * 128;
-    s.w_hi = o; o += (N1 / 8) * s.P_w;
-    s.w_lo = o; o += BF16 ? 0 : (N1 / 8) * s.P_w;
-    s.d_hi = o; o += (kTileM / 8) * s.P_d;
-    s.d_lo = o; o += BF16 ? 0 : (kTileM / 8) * s.P_d;
-    s.x_hi = o; o += (kTileM / 8) * s.P_x;   // also absorbs the MN-major over-read of the gradient operand (see kernel)
-    s.x_lo = o; o += BF16 ? 0 : (kTileM / 8) * s.P_x;
-    s.tile_d = ((kTileM * HC * elem + 127) / 128) * 128;
+    s.P_w = (OP / 8) * 128; s.P_d = (OP / 8) * 128; s.P_x = (NP2 / 8) * 128;
+    s.w_bytes = (N1 / 8) * s.P_w; s.d_bytes = (kTileM / 8) * s.P_d; s.x_bytes = (kTileM / 8) * s.P_x;
+    s.w = o; o += SPLIT * s.w_bytes;
+    s.d = o; o += SPLIT * s.d_bytes;
+    s.x = o; o += SPLIT * s.x_bytes;          // also absorbs the MN-major over-read of the gradient operand (M = 128 > 2*HC)
+    s.tile_d = ((kTileM * HC * esz + 127) / 128) * 128;
     s.tile_x = ((kTileM * F * 4 + 127) / 128) * 128;
     s.stage_bytes = 2 * s.tile_d + s.tile_x;
     s.stage0 = o; o += stages * s.stage_bytes;
@@ -371,13 +376,48 @@ __host__ __device__ inline TcBwdSmem tc_bwd_smem(int F, int HC, int OP, int N1, 
     return s;
 }
 
-template <bool BF16>
+// One row -> canonical bf16 chunks; SPLIT = 3 writes the three split terms to base, base + stride, base + 2*stride.
+template <int SPLIT, typename LoadFn>
+__device__ __forceinline__ void write_row_bf16(unsigned char *base, uint32_t split_stride, int r, uint32_t P, int n, int KP,
+                                               LoadFn load) {
+    for (int kc = 0; kc < KP / 8; ++kc) {
+        uint32_t w0[4], w1[4], w2[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int k = kc * 8 + 2 * i;
+            const float v0 = k < n ? load(k) : 0.f;
+            const float v1 = k + 1 < n ? load(k + 1) : 0.f;
+            __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+            w0[i] = *reinterpret_cast<uint32_t *>(&h);
+            if (SPLIT == 3) {
+                const float2 hf = __bfloat1622float2(h);
+                const float r0 = v0 - hf.x, r1 = v1 - hf.y;                 // exact
+                __nv_bfloat162 m = __floats2bfloat162_rn(r0, r1);
+                const float2 mf = __bfloat1622float2(m);
+                __nv_bfloat162 l = __floats2bfloat162_rn(r0 - mf.x, r1 - mf.y);
+                w1[i] = *reinterpret_cast<uint32_t *>(&m);
+                w2[i] = *reinterpret_cast<uint32_t *>(&l);
+            }
+        }
+        const uint32_t off = canon_off(r, kc, P);
+        *reinterpret_cast<uint4 *>(base + off) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
+        if (SPLIT == 3) {
+            *reinterpret_cast<uint4 *>(base + split_stride + off) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
+            *reinterpret_cast<uint4 *>(base + 2 * split_stride + off) = make_uint4(w2[0], w2[1], w2[2], w2[3]);
+        }
+    }
+}
+
+// the products kept by the split GEMM, smallest first: (a-term, b-term)
+__device__ __constant__ int kSplitPairs[6][2] = {{0, 2}, {2, 0}, {1, 1}, {0, 1}, {1, 0}, {0, 0}};
+
+template <int SPLIT>
 __global__ void __launch_bounds__(kBwdThreads, 1) project_bwd_tc_kernel(const TcBwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
-    using ST = typename std::conditional<BF16, __nv_bfloat16, float>::type;
+    using ST = typename std::conditional<SPLIT == 1, __nv_bfloat16, float>::type;
     const int F = a.F, HC = a.HC, O = 2 * a.HC, OP = a.OP, N1 = a.N1, NP2 = a.NP2, nst = a.stages;
     const bool need_dx = a.dx != nullptr;
-    const TcBwdSmem L = tc_bwd_smem<BF16>(F, HC, OP, N1, NP2, nst);
+    const TcBwdSmem L = tc_bwd_smem<SPLIT>(F, HC, OP, N1, NP2, nst);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bars);
     uint64_t *full = bars, *empty = bars + kBwdMaxStages;
     uint64_t *ops_ready = bars + 2 * kBwdMaxStages, *ops_free = ops_ready + 1;
@@ -404,7 +444,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) project_bwd_tc_kernel(const Tc
     if (warp == 1) tmem_alloc(tmem_ptr, a.tmem_cols);
     // B operand of GEMM1: B1[n = f][k = o] = Wcat[o][f]  (K-major), zero padded
     for (int n = tid; n < N1; n += kBwdThreads) {
-        write_row_canonical<BF16>(smem + L.w_hi, smem + L.w_lo, n, L.P_w, n < F ? O : 0, OP, [&](int o) {
+        write_row_bf16<SPLIT>(smem + L.w, L.w_bytes, n, L.P_w, n < F ? O : 0, OP, [&](int o) {
             return o < HC ? a.wl[(int64_t)o * F + n] : a.wr[(int64_t)(o - HC) * F + n];
         });
     }
@@ -446,15 +486,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) project_bwd_tc_kernel(const Tc
         }
     } else if (warp == 1) {
         // ===== MMA issuer ==============================================================================================
-        const uint32_t fmt = BF16 ? kFmtBF16 : kFmtTF32;
-        const uint32_t idesc1 = umma_idesc(fmt, kTileM, N1, 0, 0);
-        const uint32_t idesc2 = umma_idesc(fmt, kTileM, NP2, 1, 1);
-        const uint32_t w_hi = smem_u32(smem + L.w_hi), w_lo = smem_u32(smem + L.w_lo);
-        const uint32_t d_hi = smem_u32(smem + L.d_hi), d_lo = smem_u32(smem + L.d_lo);
-        const uint32_t x_hi = smem_u32(smem + L.x_hi), x_lo = smem_u32(smem + L.x_lo);
-        const int ksteps1 = BF16 ? OP / 16 : OP / 8;         // K = gradient columns, 32 bytes per MMA
-        const int ksteps2 = BF16 ? kTileM / 16 : kTileM / 8;  // K = rows: 8 (tf32) / 16 (bf16) rows per MMA
-        const uint32_t kb = BF16 ? 2 : 1;                     // 8-row blocks per MMA
+        const uint32_t idesc1 = umma_idesc(kFmtBF16, kTileM, N1, 0, 0);   // A, B K-major
+        const uint32_t idesc2 = umma_idesc(kFmtBF16, kTileM, NP2, 1, 1);  // A, B MN-major (the same buffers, transposed view)
+        const uint32_t w0 = smem_u32(smem + L.w), d0 = smem_u32(smem + L.d), x0 = smem_u32(smem + L.x);
+        const int ksteps1 = OP / 16;      // K = gradient columns, 16 per MMA = two 16-byte chunks
+        const int ksteps2 = kTileM / 16;  // K = rows, 16 per MMA = two 8-row blocks
+        const int nprod = SPLIT == 3 ? 6 : 1;
         const uint32_t d2 = tmem_base + a.d2_col;
         uint32_t acc2 = 0;
         for (int it = 0; it < n_local; ++it) {
@@ -467,27 +504,23 @@ __global__ void __launch_bounds__(kBwdThreads, 1) project_bwd_tc_kernel(const Tc
                     uint32_t acc = 0;
                     for (int ks = 0; ks < ksteps1; ++ks) {
                         const uint32_t ko = ks * 256;
-                        if (BF16) {
-                            umma_bf16(d1, umma_desc(d_hi + ko, 128, L.P_d), umma_desc(w_hi + ko, 128, L.P_w), idesc1, acc);
-                        } else {
-                            umma_tf32(d1, umma_desc(d_lo + ko, 128, L.P_d), umma_desc(w_hi + ko, 128, L.P_w), idesc1, acc);
-                            umma_tf32(d1, umma_desc(d_hi + ko, 128, L.P_d), umma_desc(w_lo + ko, 128, L.P_w), idesc1, 1);
-                            umma_tf32(d1, umma_desc(d_hi + ko, 128, L.P_d), umma_desc(w_hi + ko, 128, L.P_w), idesc1, 1);
+                        for (int q = 0; q < nprod; ++q) {
+                            const int ia = SPLIT == 3 ? kSplitPairs[q][0] : 0, ib = SPLIT == 3 ? kSplitPairs[q][1] : 0;
+                            umma_bf16(d1, umma_desc(d0 + ia * L.d_bytes + ko, 128, L.P_d),
+                                      umma_desc(w0 + ib * L.w_bytes + ko, 128, L.P_w), idesc1, acc);
+                            acc = 1;
                         }
-                        acc = 1;
                     }
                     umma_commit(&t_full[it & 1]);
                 }
                 for (int ks = 0; ks < ksteps2; ++ks) {
-                    const uint32_t da = ks * kb * L.P_d, dbx = ks * kb * L.P_x;
-                    if (BF16) {
-                        umma_bf16(d2, umma_desc(d_hi + da, L.P_d, 128), umma_desc(x_hi + dbx, L.P_x, 128), idesc2, acc2);
-                    } else {
-                        umma_tf32(d2, umma_desc(d_lo + da, L.P_d, 128), umma_desc(x_hi + dbx, L.P_x, 128), idesc2, acc2);
-                        umma_tf32(d2, umma_desc(d_hi + da, L.P_d, 128), umma_desc(x_lo + dbx, L.P_x, 128), idesc2, 1);
-                        umma_tf32(d2, umma_desc(d_hi + da, L.P_d, 128), umma_desc(x_hi + dbx, L.P_x, 128), idesc2, 1);
+                    const uint32_t da = ks * 2 * L.P_d, dbx = ks * 2 * L.P_x;
+                    for (int q = 0; q < nprod; ++q) {
+                        const int ia = SPLIT == 3 ? kSplitPairs[q][0] : 0, ib = SPLIT == 3 ? kSplitPairs[q][1] : 0;
+                        umma_bf16(d2, umma_desc(d0 + ia * L.d_bytes + da, L.P_d, 128),
+                                  umma_desc(x0 + ib * L.x_bytes + dbx, L.P_x, 128), idesc2, acc2);
+                        acc2 = 1;
                     }
-                    acc2 = 1;
                 }
                 umma_commit(ops_free);  // both GEMMs have consumed the operand buffers
             }
@@ -514,12 +547,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) project_bwd_tc_kernel(const Tc
                 if (half == 0) {
                     const ST *gl = reinterpret_cast<const ST *>(st) + row * HC;
                     const ST *gr = reinterpret_cast<const ST *>(st + L.tile_d) + row * HC;
-                    write_row_canonical<BF16>(smem + L.d_hi, smem + L.d_lo, row, L.P_d, live ? O : 0, OP,
-                                              [&](int o) { return o < HC ? ld_elem(gl + o) : ld_elem(gr + (o - HC)); });
+                    write_row_bf16<SPLIT>(smem + L.d, L.d_bytes, row, L.P_d, live ? O : 0, OP,
+                                          [&](int o) { return o < HC ? ld_elem(gl + o) : ld_elem(gr + (o - HC)); });
                 } else {
                     const float *xrow = reinterpret_cast<const float *>(st + 2 * L.tile_d) + row * F;
-                    write_row_canonical<BF16>(smem + L.x_hi, smem + L.x_lo, row, L.P_x, live ? F + 1 : 0, NP2,
-                                              [&](int f) { return f < F ? xrow[f] : 1.f; });
+                    write_row_bf16<SPLIT>(smem + L.x, L.x_bytes, row, L.P_x, live ? F + 1 : 0, NP2,
+                                          [&](int f) { return f < F ? xrow[f] : 1.f; });
                 }
                 fence_proxy_async();
                 mbar_arrive(ops_ready);
@@ -588,9 +621,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) project_bwd_tc_kernel(const Tc
     }
 }
 
-template <bool BF16>
+template <int SPLIT>
 static bool bwd_tc_config(TcBwdArgs &a) {
-    a.OP = BF16 ? ((2 * a.HC + 15) / 16) * 16 : ((2 * a.HC + 7) / 8) * 8;
+    a.OP = ((2 * a.HC + 15) / 16) * 16;
     a.N1 = ((a.F + 15) / 16) * 16;
     a.NP2 = ((a.F + 1 + 15) / 16) * 16;
     if (2 * a.HC > 128 || a.N1 > 256 || a.NP2 > 256) return false;
@@ -599,14 +632,14 @@ static bool bwd_tc_config(TcBwdArgs &a) {
     a.tmem_cols = pow2_cols(a.d2_col + a.NP2);
     if (a.tmem_cols > 512) return false;
     for (a.stages = kBwdMaxStages; a.stages >= 1; --a.stages)
-        if (tc_bwd_smem<BF16>(a.F, a.HC, a.OP, a.N1, a.NP2, a.stages).total <= 220u * 1024u) return true;
+        if (tc_bwd_smem<SPLIT>(a.F, a.HC, a.OP, a.N1, a.NP2, a.stages).total <= 220u * 1024u) return true;
     return false;
 }
 
 bool project_bwd_tc_supported(int F, int HC, int dtype) {
     TcBwdArgs a{};
     a.F = F; a.HC = HC;
-    return dtype == TECGAT_BF16 ? bwd_tc_config<true>(a) : bwd_tc_config<false>(a);
+    return dtype == TECGAT_BF16 ? bwd_tc_config<1>(a) : bwd_tc_config<3>(a);
 }
 
 static int bwd_tc_grid(int64_t R) {
@@ -620,11 +653,11 @@ int64_t project_bwd_tc_workspace(int64_t R, int F, int HC) {
     return tc > ff ? tc : ff;
 }
 
-template <bool BF16>
+template <int SPLIT>
 static int launch_bwd_tc(TcBwdArgs &a, float *dwl, float *dbl, float *dwr, float *dbr, cudaStream_t st) {
-    bwd_tc_config<BF16>(a);
-    const TcBwdSmem L = tc_bwd_smem<BF16>(a.F, a.HC, a.OP, a.N1, a.NP2, a.stages);
-    auto kern = project_bwd_tc_kernel<BF16>;
+    bwd_tc_config<SPLIT>(a);
+    const TcBwdSmem L = tc_bwd_smem<SPLIT>(a.F, a.HC, a.OP, a.N1, a.NP2, a.stages);
+    auto kern = project_bwd_tc_kernel<SPLIT>;
     TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     const int grid = bwd_tc_grid(a.R);
     kern<<<grid, kBwdThreads, L.total, st>>>(a);
@@ -644,7 +677,7 @@ int project_bwd_tc(const void *dxl, const void *dxr, const float *x, const float
     TcBwdArgs a{};
     a.dxl = dxl; a.dxr = dxr; a.x = x; a.wl = wl; a.wr = wr; a.dx = dx; a.partials = static_cast<float *>(workspace);
     a.R = R; a.F = F; a.HC = HC;
-    return dtype == TECGAT_BF16 ? launch_bwd_tc<true>(a, dwl, dbl, dwr, dbr, st) : launch_bwd_tc<false>(a, dwl, dbl, dwr, dbr, st);
+    return dtype == TECGAT_BF16 ? launch_bwd_tc<1>(a, dwl, dbl, dwr, dbr, st) : launch_bwd_tc<3>(a, dwl, dbl, dwr, dbr, st);
 }
 
 }  // namespace tg

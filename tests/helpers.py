@@ -51,7 +51,7 @@ def kernel_dropout_mask(plan, snapshots, heads, p, seed, mode="shared"):
     kept = plan.kept_edges
     _, _, eid = plan.export()
     keep = np.empty((snapshots * E, heads), dtype=np.uint8)
-    _lib.call("tecgat_dropout_mask_host", C.c_uint64(seed), 0, snapshots * E, heads, C.c_float(p),
+    _lib.call("tecgat_dropout_mask_host", C.c_uint64(seed), 0, snapshots * E, heads, C.c_float(p), E,
               C.c_void_p(keep.ctypes.data))
     keep = keep.reshape(snapshots, E, heads)
     eid = eid.astype(np.int64)

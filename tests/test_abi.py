@@ -57,26 +57,32 @@ def test_dropout_mask_host_statistics(lib):
 
     n, H, p = 200000, 2, 0.1
     keep = np.empty((n, H), dtype=np.uint8)
-    _lib.call("tecgat_dropout_mask_host", C.c_uint64(1234), 0, n, H, C.c_float(p), C.c_void_p(keep.ctypes.data))
+    E = 23835
+    _lib.call("tecgat_dropout_mask_host", C.c_uint64(1234), 0, n, H, C.c_float(p), E, C.c_void_p(keep.ctypes.data))
     rate = 1.0 - keep.mean()
     assert abs(rate - p) < 4e-3
     assert abs(keep[:, 0].mean() - keep[:, 1].mean()) < 6e-3
     keep2 = np.empty_like(keep)
-    _lib.call("tecgat_dropout_mask_host", C.c_uint64(1234), 0, n, H, C.c_float(p), C.c_void_p(keep2.ctypes.data))
+    _lib.call("tecgat_dropout_mask_host", C.c_uint64(1234), 0, n, H, C.c_float(p), E, C.c_void_p(keep2.ctypes.data))
     assert np.array_equal(keep, keep2)                      # counter-based: reproducible
-    _lib.call("tecgat_dropout_mask_host", C.c_uint64(1235), 0, n, H, C.c_float(p), C.c_void_p(keep2.ctypes.data))
+    _lib.call("tecgat_dropout_mask_host", C.c_uint64(1235), 0, n, H, C.c_float(p), E, C.c_void_p(keep2.ctypes.data))
     assert (keep != keep2).mean() > 0.1                     # seed matters
     # windows of the counter stream are consistent
     part = np.empty((1000, H), dtype=np.uint8)
-    _lib.call("tecgat_dropout_mask_host", C.c_uint64(1234), 5000, 1000, H, C.c_float(p), C.c_void_p(part.ctypes.data))
+    _lib.call("tecgat_dropout_mask_host", C.c_uint64(1234), 5000, 1000, H, C.c_float(p), E, C.c_void_p(part.ctypes.data))
     assert np.array_equal(part, keep[5000:6000])
+    # every snapshot gets its own stream, heads of a pair are decorrelated
+    snaps = keep[: 8 * E].reshape(8, E, H)
+    assert (snaps[0] != snaps[1]).mean() > 0.1
+    both = (1 - keep[:, 0].astype(float)) * (1 - keep[:, 1].astype(float))
+    assert abs(both.mean() - p * p) < 2e-3
 
 
 def test_errors_are_reported_not_thrown(lib):
     from tec_mollm_b200 import _lib
 
     with pytest.raises(RuntimeError, match="bad argument"):
-        _lib.call("tecgat_dropout_mask_host", C.c_uint64(0), 0, 10, 0, C.c_float(0.1), None)
+        _lib.call("tecgat_dropout_mask_host", C.c_uint64(0), 0, 10, 0, C.c_float(0.1), 5, None)
     info = (C.c_int64 * 8)()
     assert lib.tecgat_plan_info(None, info) != 0
     assert b"NULL" in lib.tecgat_last_error()
