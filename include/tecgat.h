@@ -17,7 +17,7 @@
  *
  * Row-major layouts, R = S*N rows (snapshot-major: row = s*N + node):
  *   x  (R, F)   fp32        xl, xr (R, H*C) storage dtype (fp32, or bf16 for the autocast contract)
- *   y  (R, H*C) fp32        m, den (R, H)   fp32  (softmax shift and denominator, saved for backward)
+ *   y  (R, H*C) fp32        stat   (R, H)   fp32  (log2-sum-exp of the row's scores: alpha = exp2(e - stat), saved for backward)
  */
 #ifndef TECGAT_H_
 #define TECGAT_H_
@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TECGAT_ABI_VERSION 1
+#define TECGAT_ABI_VERSION 2
 
 /* error codes */
 #define TECGAT_OK 0
@@ -56,16 +56,21 @@ const char *tecgat_last_error(void);
 
 /* ---- graph plan: replaces remove_self_loops + add_self_loops done on EVERY forward by PyG
  *      (GATv2Conv.forward, called at src/model/modules.py:356) with a one-time,
- *      cached, destination-sorted CSR (+ source-sorted CSR for the atomic-free backward and a
- *      per-tile source-row window).  Synchronises `stream` once (edge list is read back to host). */
+ *      cached structure: destination-sorted CSR + source-sorted CSR (atomic-free backward), and for the
+ *      forward and the backward kernel one tiling each of the node axis (tile_nodes_fwd / tile_nodes_bwd
+ *      consecutive nodes per tile, multiples of 8) with the tile's row window and its ELL slab.
+ *      Synchronises `stream` (the edge list is read back to the host once). */
 int tecgat_plan_create(const int64_t *edge_index_dev, int64_t num_edges, int32_t num_nodes,
-                       int32_t tile_nodes, void *stream, tecgat_plan_t **plan_out);
+                       int32_t tile_nodes_fwd, int32_t tile_nodes_bwd, void *stream,
+                       tecgat_plan_t **plan_out);
 int tecgat_plan_destroy(tecgat_plan_t *plan);
-/* info[0]=E (kept edges + N self loops) [1]=max in-degree [2]=max out-degree [3]=tiles
- * [4]=tile_nodes [5]=max source-window rows [6]=num_nodes [7]=kept (non-self) edges */
-int tecgat_plan_info(const tecgat_plan_t *plan, int64_t *info8_host);
+/* info[0]=E (kept edges + N self loops) [1]=max in-degree [2]=max out-degree [3]=forward tiles
+ * [4]=tile_nodes_fwd [5]=max forward window rows [6]=num_nodes [7]=kept (non-self) edges
+ * [8]=backward tiles [9]=tile_nodes_bwd [10]=max backward window rows [11]=0 */
+int tecgat_plan_info(const tecgat_plan_t *plan, int64_t *info12_host);
 /* Host copies for tests: rowptr (N+1), col (E) = source node of CSR slot k, eid (E) = index of that
- * edge in PyG's post-surgery edge order (kept edges in input order, then self loops). */
+ * edge in PyG's post-surgery edge order (kept edges in input order, then self loops).  Every CSR row
+ * starts with the node's self loop. */
 int tecgat_plan_export(const tecgat_plan_t *plan, int32_t *rowptr_host, int32_t *col_host,
                        int32_t *eid_host);
 
@@ -87,22 +92,21 @@ int tecgat_project_bwd(const void *dxl_dev, const void *dxr_dev, const float *x_
 /* ---- fused edge phase: replaces gather + LeakyReLU*att + segment softmax + dropout + scatter-add
  *      + bias (~20 ATen launches in PyG) with one kernel over all snapshots.
  *      dropout_p == 0 disables dropout; otherwise the keep bit of (snapshot s, CSR slot k, head h) is the
- *      counter-based hash restated by tecgat_dropout_mask_host.  negative_slope must lie in [0, 1].   */
+ *      counter-based hash restated by tecgat_dropout_mask_host.                                          */
 int tecgat_edge_fwd(const tecgat_plan_t *plan, const void *xl_dev, const void *xr_dev,
-                    const float *att_dev, const float *bias_dev, float *y_dev, float *m_dev,
-                    float *den_dev, int32_t snapshots, int32_t heads, int32_t out_channels,
-                    float negative_slope, float dropout_p, uint64_t seed, int32_t mode,
-                    int32_t dtype, void *stream);
+                    const float *att_dev, const float *bias_dev, float *y_dev, float *stat_dev,
+                    int32_t snapshots, int32_t heads, int32_t out_channels, float negative_slope,
+                    float dropout_p, uint64_t seed, int32_t mode, int32_t dtype, void *stream);
 int64_t tecgat_edge_bwd_workspace(const tecgat_plan_t *plan, int32_t snapshots, int32_t heads,
                                   int32_t out_channels);
 /* backward of the edge phase, atomic-free: every node's lane reduces its incoming edges (d xr) and its
  * outgoing edges (d xl) from the two CSR orientations; d att / d bias via deterministic two-stage sums. */
 int tecgat_edge_bwd(const tecgat_plan_t *plan, const void *xl_dev, const void *xr_dev,
                     const float *att_dev, const float *bias_dev, const float *y_dev,
-                    const float *m_dev, const float *den_dev, const float *gy_dev, void *dxl_dev,
-                    void *dxr_dev, float *datt_dev, float *dbias_dev, void *workspace_dev,
-                    int32_t snapshots, int32_t heads, int32_t out_channels, float negative_slope,
-                    float dropout_p, uint64_t seed, int32_t mode, int32_t dtype, void *stream);
+                    const float *stat_dev, const float *gy_dev, void *dxl_dev, void *dxr_dev,
+                    float *datt_dev, float *dbias_dev, void *workspace_dev, int32_t snapshots,
+                    int32_t heads, int32_t out_channels, float negative_slope, float dropout_p,
+                    uint64_t seed, int32_t mode, int32_t dtype, void *stream);
 
 /* Host restatement of the kernels' counter-based dropout RNG (pure integer arithmetic), so tests can
  * hand the oracle exactly the mask the kernels used.  Global slot g = snapshot * edges_per_snapshot + CSR slot;

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libtecgat.so")
 F32, BF16 = 0, 1
 MODE_SHARED, MODE_LITERAL = 0, 1
 PROJ_TC, PROJ_FFMA = 0, 1
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _lock = threading.Lock()
 _lib = None
@@ -27,16 +27,16 @@ _vp, _i32, _i64, _u64, _f32, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64
 _SIGNATURES = {
     "tecgat_abi_version": (C.c_int, []),
     "tecgat_last_error": (C.c_char_p, []),
-    "tecgat_plan_create": (C.c_int, [_vp, _i64, _i32, _i32, _vp, C.POINTER(_vp)]),
+    "tecgat_plan_create": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, C.POINTER(_vp)]),
     "tecgat_plan_destroy": (C.c_int, [_vp]),
     "tecgat_plan_info": (C.c_int, [_vp, C.POINTER(_i64)]),
     "tecgat_plan_export": (C.c_int, [_vp, _vp, _vp, _vp]),
     "tecgat_project_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp]),
     "tecgat_project_bwd_workspace": (_i64, [_i64, _i32, _i32, _i32]),
     "tecgat_project_bwd": (C.c_int, [_vp] * 11 + [_i64, _i32, _i32, _i32, _i32, _vp]),
-    "tecgat_edge_fwd": (C.c_int, [_vp] * 8 + [_i32, _i32, _i32, _f32, _f32, _u64, _i32, _i32, _vp]),
+    "tecgat_edge_fwd": (C.c_int, [_vp] * 7 + [_i32, _i32, _i32, _f32, _f32, _u64, _i32, _i32, _vp]),
     "tecgat_edge_bwd_workspace": (_i64, [_vp, _i32, _i32, _i32]),
-    "tecgat_edge_bwd": (C.c_int, [_vp] * 14 + [_i32, _i32, _i32, _f32, _f32, _u64, _i32, _i32, _vp]),
+    "tecgat_edge_bwd": (C.c_int, [_vp] * 13 + [_i32, _i32, _i32, _f32, _f32, _u64, _i32, _i32, _vp]),
     "tecgat_dropout_mask_host": (C.c_int, [_u64, _i64, _i64, _i32, _f32, _i64, _vp]),
     "tecgraph_distance_rows": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _f64, _vp, _vp]),
     "tecgraph_edges_count": (C.c_int, [_vp, _vp, _i64, _f64, _f64, _vp, C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_i64)]),

@@ -7,6 +7,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <vector>
 
 #include "tecgat.h"
 
@@ -34,23 +35,47 @@ void tecgat_set_error(const char *fmt, ...);
 
 #define TG_LAUNCH_CHECK() TG_CUDA(cudaGetLastError())
 
+// One tiling of the node axis: tiles of T consecutive nodes, each with the contiguous row window [lo, hi) it touches and
+// a "slab" -- the tile's slice of the graph in ELL form, laid out so that ONE bulk-TMA copy brings it into shared memory:
+//   (Ts = T rounded up to a multiple of 8 is the row stride of every section below)
+//   header  16 B : int32 {lo, hi, kin | kout << 16, slot_base}
+//   k0      T x int32 : first in-CSR slot of node t        (dropout counter of its k-th in-edge = k0 + k)
+//   deg     T x int32 : in-degree | out-degree << 16        (0 for the padding nodes of a ragged last tile)
+//   ell_in  kin  x T x uint16 : window-relative row (col - lo) of the k-th in-neighbour   (self loop is k = 0; kin and
+//                               kout are padded to ODD counts, unused entries are 0 = a valid window row)
+//   -- backward tilings only --
+//   ell_out kout x T x uint16 : window-relative row of the k-th out-neighbour
+//   slot    kout x T x uint16 : in-CSR slot of that edge, relative to slot_base = rowptr_in[lo]
+struct tg_tile_meta {  // 32 bytes; the kernels keep the table in shared memory
+    int32_t lo, hi;
+    int32_t kin_kout;  // kin | kout << 16
+    int32_t eligible;  // 1: the slab exists (indices fit uint16)
+    int64_t slab_off;  // byte offset of the tile's slab
+    int32_t slab_bytes;
+    int32_t pad;
+};
+struct tg_tiling {
+    int32_t T = 0, num_tiles = 0, max_window = 0;
+    bool bwd = false;
+    tg_tile_meta *meta = nullptr;  // device (tiles)
+    unsigned char *slabs = nullptr;  // device
+    std::vector<tg_tile_meta> h_meta;
+    std::vector<int64_t> h_slab_off;  // (tiles + 1)
+};
+
 struct tecgat_plan {
     int32_t num_nodes = 0;
-    int32_t tile_nodes = 0;
-    int32_t num_tiles = 0;
     int64_t num_edges = 0;   // kept edges + N self loops
     int64_t kept_edges = 0;  // non-self edges of the input
     int32_t max_in_deg = 0;
     int32_t max_out_deg = 0;
-    int32_t max_window = 0;  // max over tiles of (hi - lo)
-    // device arrays (int32)
+    // device arrays (int32): the two CSR orientations; every row starts with the node's self loop
     int32_t *rowptr_in = nullptr;  // (N+1) destination-sorted CSR
     int32_t *col_in = nullptr;     // (E)   source node of slot k
     int32_t *rowptr_out = nullptr; // (N+1) source-sorted CSR
     int32_t *col_out = nullptr;    // (E)   destination node of out-slot k2
     int32_t *slot_out = nullptr;   // (E)   in-CSR slot k of out-slot k2 (dropout counter)
-    int32_t *tile_lo = nullptr;    // (tiles) first row of the tile's source/destination window
-    int32_t *tile_hi = nullptr;    // (tiles) one past the last row of the window
+    tg_tiling fwd, bwd;
     // host copies kept for export / tests
     int32_t *h_rowptr_in = nullptr;
     int32_t *h_col_in = nullptr;
@@ -173,9 +198,9 @@ __device__ __forceinline__ void st_elem(float *p, float v) { *p = v; }
 __device__ __forceinline__ void st_elem(__nv_bfloat16 *p, float v) { *p = __float2bfloat16_rn(v); }
 
 // ---- counter-based dropout RNG: integer-only, restated on the host (tecgat_dropout_mask_host) -----------------
-// keep(seed, snapshot, CSR slot, head).  The 64-bit seed and the snapshot index are folded ONCE per CTA into a 32-bit
-// per-snapshot key; per (slot, head pair) one murmur3-style 32-bit finaliser (3 multiplies, 3 xor-shifts) yields two
-// 16-bit uniforms, one per head of the pair.  P(drop) = round(p * 65536) / 65536.
+// keep(seed, snapshot, CSR slot, head).  The 64-bit seed, the snapshot and the head are folded ONCE per (item, lane)
+// into a well-mixed 32-bit key; per edge one multiply-add, one xor-shift and one multiply produce 32 uniform bits
+// that are compared against round(p * 2^32):  6 integer instructions per (edge, head).
 __host__ __device__ __forceinline__ uint32_t fmix32(uint32_t h) {
     h ^= h >> 16;
     h *= 0x85EBCA6Bu;
@@ -184,18 +209,26 @@ __host__ __device__ __forceinline__ uint32_t fmix32(uint32_t h) {
     h ^= h >> 16;
     return h;
 }
-__host__ __device__ __forceinline__ uint32_t dropout_snapshot_key(uint64_t seed, uint32_t snapshot) {
+__host__ __device__ __forceinline__ uint32_t dropout_snapshot_key(uint64_t seed, uint32_t snapshot) {  // once per snapshot
     return fmix32(static_cast<uint32_t>(seed) ^ fmix32(static_cast<uint32_t>(seed >> 32) + 0x9E3779B9u * (snapshot + 1u)));
 }
-__host__ __device__ __forceinline__ uint32_t dropout_bits16(uint32_t key, uint32_t slot, uint32_t head) {
-    const uint32_t h = fmix32((slot * 0x9E3779B1u) ^ key ^ ((head >> 1) * 0x7FEB352Du));
-    return (h >> ((head & 1u) * 16u)) & 0xFFFFu;
+__host__ __device__ __forceinline__ uint32_t dropout_head_key(uint32_t head) {  // once per lane
+    return fmix32(0x7FEB352Du * (head + 1u));
+}
+__host__ __device__ __forceinline__ uint32_t dropout_key(uint64_t seed, uint32_t snapshot, uint32_t head) {
+    return dropout_snapshot_key(seed, snapshot) ^ dropout_head_key(head);
+}
+__host__ __device__ __forceinline__ uint32_t dropout_bits(uint32_t key, uint32_t slot) {
+    uint32_t h = slot * 0x9E3779B1u + key;
+    h ^= h >> 15;
+    h *= 0x85EBCA6Bu;
+    return h;
 }
 __host__ __device__ __forceinline__ uint32_t dropout_threshold(float p) {
-    // keep iff bits16 >= thr;  P(drop) = thr / 65536
-    double t = static_cast<double>(p) * 65536.0;
+    // keep iff bits >= thr;  P(drop) = thr / 2^32
+    double t = static_cast<double>(p) * 4294967296.0;
     if (t < 0) t = 0;
-    if (t > 65536.0) t = 65536.0;
+    if (t > 4294967295.0) t = 4294967295.0;
     return static_cast<uint32_t>(t + 0.5);
 }
 

@@ -1,13 +1,22 @@
 // edge_bwd.cu -- fused GATv2 edge phase, backward, atomic-free (formulas section 8a-3, restated and
 // gradient-checked in oracle/gatv2_oracle.py::gatv2_backward_manual).  With g = dL/dy, delta_i = g_i . (y_i - bias),
-// q = keep/(1-p):
-//     alpha_ij = exp(e_ij - m_i) / den_i                 (recomputed from xl_j, xr_i and the saved m, den)
+// q = keep/(1-p), s_ij = xl_j + xr_i, sgn(s) = +1 if s > 0 else -1:
+//     alpha_ij = exp2(e_ij - stat_i)                        (recomputed from xl_j, xr_i and the saved log-sum-exp)
 //     de_ij    = alpha_ij (q_ij g_i.xl_j - delta_i)
-//     d xr_i   = sum_{j -> i} de_ij att * lrelu'(s_ij)                          (lane's role as DESTINATION)
-//     d xl_j   = sum_{j -> i} alpha_ij q_ij g_i + de_ij att * lrelu'(s_ij)      (lane's role as SOURCE)
-//     d att    = sum_ij de_ij lrelu(s_ij),   d bias = sum_i g_i
-// One lane owns one (node, head) and walks BOTH CSR orientations, so each gradient row has exactly one writer:
-// no atomics, bit-reproducible.  d att / d bias: per-CTA partials + a fixed-order fp64 second stage.
+//     d xr_i   = att_p A_i + att_m Bs_i,        A_i = sum_j de_ij,  Bs_i[c] = sum_j de_ij sgn(s_ij[c])   (DESTINATION role)
+//     d xl_j   = sum_i alpha_ij q_ij g_i + att_p A'_j + att_m Bs'_j                                    (SOURCE role)
+//     d att    = (1+slope)/2 sum_rows (xl_v A'_v + xr_v A_v) + (1-slope)/2 sum_ij de_ij |s_ij|,   d bias = sum_i g_i
+// (att_p = att (1+slope)/2, att_m = att (1-slope)/2: LeakyReLU' = (1+slope)/2 + (1-slope)/2 sgn(s), slope at s = 0.)
+// One lane owns one (node, head) and walks BOTH CSR orientations, so every gradient row has exactly one writer: no
+// atomics, bit-reproducible.  d att / d bias: per-lane fp64 accumulators across the CTA's items, one fixed-order
+// cross-lane reduction per CTA at the end, then a fixed-order fp64 second stage over the CTAs (reduce.cu).
+// Execution model, lane mapping and arithmetic: edge_common.cuh.
+#include <algorithm>
+#include <cstdlib>
+#include <type_traits>
+#include <utility>
+#include <vector>
+
 #include "edge_common.cuh"
 #include "reduce.cuh"
 
@@ -15,288 +24,570 @@ namespace tg {
 
 struct EdgeBwdArgs {
     const void *xl, *xr;
-    const float *att, *bias, *y, *m, *den, *gy;
+    const float *att, *bias, *y, *stat, *gy;
     void *dxl, *dxr;
     float *partials;  // (grid, 2*HC): [d att | d bias] per CTA
-    const int32_t *rowptr_in, *col_in, *rowptr_out, *col_out, *slot_out, *tile_lo, *tile_hi;
-    int32_t N, T, num_tiles, S, H;
-    int64_t E;
+    const tg_tile_meta *meta;
+    const unsigned char *slabs;
+    const int32_t *rowptr_in, *col_in, *rowptr_out, *col_out, *slot_out;  // tiles that are not staged
+    int32_t N, T, num_tiles, S, H, npw;
     float slope, inv_keep;
     uint32_t drop_thr;
     uint64_t seed;
     int32_t literal;
-    int32_t win_rows_smem;  // windows up to this many rows are staged in shared memory
-    int32_t region_rows;    // rows each shared region is sized for (>= T)
+    int32_t cap_rows, cap_kin, cap_kout, num_stages;
+    int32_t per_st, per_f, per_stat;  // 16-byte row periods (rows) of xl/xr, of g/y and of stat
+    // shared-memory map (bytes): [barriers 128][tile table][y window][out staging][stage 0][stage 1]..
+    // stage: [slab][stat window raw][delta|stat planes (H x cap_rows float2)][xl window][xr window][g window]
+    uint32_t stage_bytes, off_meta, off_stage0, off_y, off_out, off_statraw, off_ds, off_xl, off_xr, off_g;
+    int64_t items;
 };
 
-template <int C, typename ST, bool SM>
-__device__ __forceinline__ void edge_bwd_body(const EdgeBwdArgs &a, unsigned char *smem_raw) {
-    const int tid = threadIdx.x;
-    const int tile = blockIdx.x % a.num_tiles;
-    const int snap = blockIdx.x / a.num_tiles;
-    const int H = a.H, HC = H * C;
-    const int n0 = tile * a.T;
-    const int n1 = min(a.N, n0 + a.T);
-    const int nt = n1 - n0;
-    const bool self_only = a.literal && snap > 0;
-    int lo = a.tile_lo[tile], hi = a.tile_hi[tile];
-    if (self_only) { lo = n0; hi = n1; }
-    const int win = hi - lo;
-    const int64_t row0 = static_cast<int64_t>(snap) * a.N + lo;  // global row of window row 0
+constexpr int kBarConsumers = 1;  // named barrier id used by the consumer warps
 
-    const ST *xl_g = static_cast<const ST *>(a.xl) + row0 * HC;
-    const ST *xr_g = static_cast<const ST *>(a.xr) + row0 * HC;
-    const float *g_g = a.gy + row0 * HC;
-    const float *y_g = a.y + row0 * HC;
-    const float *m_g = a.m + row0 * H;
-    const float *den_g = a.den + row0 * H;
+__device__ __forceinline__ void bar_sync_named(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
 
-    // shared layout: [mbarrier 16][xl region][xr region][g region][y region][m | inv_den | delta]
-    const uint32_t reg_st = round16(a.region_rows * HC * (uint32_t)sizeof(ST)) + 16;
-    const uint32_t reg_f = round16(a.region_rows * HC * (uint32_t)sizeof(float)) + 16;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
-    unsigned char *xl_base = smem_raw + 16;
-    unsigned char *xr_base = xl_base + reg_st;
-    unsigned char *g_base = xr_base + reg_st;
-    unsigned char *y_base = g_base + reg_f;
-    float *m_s = reinterpret_cast<float *>(y_base + reg_f);
-    float *inv_s = m_s + a.region_rows * H;
-    float *delta_s = inv_s + a.region_rows * H;
-
-    const ST *xl_w = xl_g, *xr_w = xr_g;  // window accessors: shared (SM) or global (fallback)
-    const float *g_w = g_g;
-    if (SM) {
-        const uint32_t nb_st = win * HC * (uint32_t)sizeof(ST), nb_f = win * HC * (uint32_t)sizeof(float);
-        const CopyPlan c0 = plan_copy(xl_g, xl_base, nb_st);
-        const CopyPlan c1 = plan_copy(xr_g, xr_base, nb_st);
-        const CopyPlan c2 = plan_copy(g_g, g_base, nb_f);
-        const CopyPlan c3 = plan_copy(y_g, y_base, nb_f);
-        if (tid == 0) {
-            mbar_init(bar, 1);
-            fence_mbar_init();
-        }
-        __syncthreads();
-        if (tid == 0) {
-            mbar_arrive_expect_tx(bar, c0.mid + c1.mid + c2.mid + c3.mid);
-            issue_copy_bulk(c0, bar);
-            issue_copy_bulk(c1, bar);
-            issue_copy_bulk(c2, bar);
-            issue_copy_bulk(c3, bar);
-        }
-        copy_ragged(c0, tid);
-        copy_ragged(c1, tid);
-        copy_ragged(c2, tid);
-        copy_ragged(c3, tid);
-        __syncthreads();
-        mbar_wait(bar, 0);
-        xl_w = reinterpret_cast<const ST *>(c0.s);
-        xr_w = reinterpret_cast<const ST *>(c1.s);
-        g_w = reinterpret_cast<const float *>(c2.s);
-        const float *y_w = reinterpret_cast<const float *>(c3.s);
-        // per (window row, head): m, 1/den, delta = g . (y - bias)
-        for (int i = tid; i < win * H; i += blockDim.x) {
-            const int r = i / H, hh = i - r * H;
-            const float *gp = g_w + r * HC + hh * C, *yp = y_w + r * HC + hh * C;
-            float dl = 0.f;
+// sgn-weighted accumulate:  B[c] += de * [s[c] > 0]
+template <int C>
+__device__ __forceinline__ void acc_step(CV<C> &B, const CV<C> &s, float de) {
+    const float2 de2 = splat(de);
 #pragma unroll
-            for (int c = 0; c < C; ++c) dl = fmaf(gp[c], yp[c] - __ldg(a.bias + hh * C + c), dl);
-            delta_s[i] = dl;
-            m_s[i] = m_g[i];
-            inv_s[i] = 1.f / den_g[i];
-        }
-        __syncthreads();
+    for (int i = 0; i < CV<C>::NP; ++i) {
+        const float2 step = make_float2(s.p[i].x > 0.f ? 1.f : 0.f, s.p[i].y > 0.f ? 1.f : 0.f);
+        B.p[i] = __ffma2_rn(de2, step, B.p[i]);
     }
-
-    constexpr int CP = (C + 1) / 2;
-    constexpr float kLog2e = 1.4426950408889634f;
-    const int node_l = tid / H;
-    const int h = tid - node_l * H;
-    const bool active = node_l < nt;
-    float2 dxl[CP], dxr[CP], datt[CP];
+    if (CV<C>::ODD) B.s = fmaf(de, s.s > 0.f ? 1.f : 0.f, B.s);
+}
+template <int C>
+__device__ __forceinline__ void cv_axpy(CV<C> &y, float a, const CV<C> &x) {
+    const float2 a2 = splat(a);
 #pragma unroll
-    for (int i = 0; i < CP; ++i) dxl[i] = dxr[i] = datt[i] = make_float2(0.f, 0.f);
+    for (int i = 0; i < CV<C>::NP; ++i) y.p[i] = __ffma2_rn(a2, x.p[i], y.p[i]);
+    if (CV<C>::ODD) y.s = fmaf(a, x.s, y.s);
+}
 
+struct DropCfg {
+    uint32_t thr, key;
+    float inv_keep;
+    __device__ __forceinline__ float q(uint32_t slot) const {
+        if (!thr) return 1.f;
+        return dropout_bits(key, slot) >= thr ? inv_keep : 0.f;
+    }
+};
+
+// score of an out-edge (v -> u) from the source's side:  c1 + att_m . |xl_v + xr_u|   (c1 = att_p . xl_v)
+template <int C>
+__device__ __forceinline__ float out_score(const CV<C> &attm, float c1, const CV<C> &xl_v, const CV<C> &xru, CV<C> &s) {
+    float2 ea = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < CV<C>::NP; ++i) {
+        s.p[i] = __fadd2_rn(xl_v.p[i], xru.p[i]);
+        ea = __ffma2_rn(attm.p[i], abs2(s.p[i]), ea);
+    }
+    float e = c1 + (ea.x + ea.y);
+    if (CV<C>::ODD) {
+        s.s = xl_v.s + xru.s;
+        e = fmaf(attm.s, fabsf(s.s), e);
+    }
+    return e;
+}
+
+// Everything one lane = (node v, head) does for one item.  The self loop (slot 0 of both CSR rows, the same edge) is
+// evaluated once and feeds both roles; the remaining in- and out-slots are walked two per iteration, branch-free
+// (slots past the degree read a valid row and get weight 0).
+//   NbrIn(k) / NbrOut(k): row index of the k-th in- / out-neighbour relative to the base pointers
+//   SlotOut(k): in-CSR slot (dropout counter) of the k-th out-edge;  DsOf(u, gu): (delta_u, stat_u)
+template <int C, typename ST, bool VEC, class NbrIn, class NbrOut, class SlotOut, class DsOf>
+__device__ __forceinline__ void bwd_lane(const CV<C> &attp, const CV<C> &attm, const CV<C> &att, float slope, const DropCfg &drop,
+                                         const ST *xl_base, const ST *xr_base, const float *g_base, int HC, int par, ptrdiff_t vrow,
+                                         float2 dv, int deg_in, int kmax_in, int deg_out, int kmax_out, uint32_t slot0,
+                                         NbrIn nbr_in, NbrOut nbr_out, SlotOut slot_out, DsOf ds_of, bool active, CV<C> &dxl,
+                                         CV<C> &dxr, CV<C> &tatt, CV<C> &g_v) {
+    CV<C> xl_v, xr_v, B_in, B_out, G;
     if (active) {
-        const int v = n0 + node_l;
-        const int vl = v - lo;
-        float2 xl_v[CP], xr_v[CP], g_v[CP], att_h[CP];
-        load_row<C>(xl_w + vl * HC + h * C, xl_v);
-        load_row<C>(xr_w + vl * HC + h * C, xr_v);
-        load_row<C>(g_w + vl * HC + h * C, g_v);
-        load_row<C>(a.att + h * C, att_h);
-        float m_v, inv_v, delta_v;
-        if (SM) {
-            m_v = m_s[vl * H + h];
-            inv_v = inv_s[vl * H + h];
-            delta_v = delta_s[vl * H + h];
-        } else {
-            m_v = m_g[vl * H + h];
-            inv_v = 1.f / den_g[vl * H + h];
-            float2 yv[CP], bh[CP], d2 = make_float2(0.f, 0.f);
-            load_row<C>(y_g + vl * HC + h * C, yv);
-            load_row<C>(a.bias + h * C, bh);
+        cv_load<C, VEC>(xl_v, xl_base + vrow * HC, par);
+        cv_load<C, VEC>(xr_v, xr_base + vrow * HC, par);
+        cv_load<C, VEC>(g_v, g_base + vrow * HC, par);
+    } else {
+        cv_zero(xl_v);
+        cv_zero(xr_v);
+        cv_zero(g_v);
+    }
+    cv_zero(B_in);
+    cv_zero(B_out);
+    cv_zero(G);
+    float A_in, A_out;
+    {   // ---- self loop --------------------------------------------------------------------------------------------
+        CV<C> s;
+        const float e = edge_score<C>(attp, attm, xl_v, xr_v, s);
+        const float gx = cv_dot<C>(g_v, xl_v);
+        const float q = drop.q(slot0);
+        const float alpha = (active ? 1.f : 0.f) * fast_exp2(fminf(e - dv.y, 100.f));
+        const float de = alpha * fmaf(q, gx, -dv.x);
+        A_in = A_out = de;
+        acc_step<C>(B_in, s, de);
+        B_out = B_in;
+        cv_axpy<C>(G, alpha * q, g_v);
+    }
+    // ---- role 1: v as DESTINATION, in-edges (u -> v): A_in, B_in ------------------------------------------------
+#pragma unroll 1
+    for (int k = 1; k < kmax_in; k += 2) {
+        const ptrdiff_t ua = nbr_in(k), ub = nbr_in(k + 1);
+        CV<C> xa, xb, sa, sb;
+        cv_load<C, VEC>(xa, xl_base + ua * HC, par);
+        cv_load<C, VEC>(xb, xl_base + ub * HC, par);
+        const float ea = edge_score<C>(attp, attm, xa, xr_v, sa);
+        const float eb = edge_score<C>(attp, attm, xb, xr_v, sb);
+        const float ga = cv_dot<C>(g_v, xa), gb = cv_dot<C>(g_v, xb);
+        const float va = k < deg_in ? 1.f : 0.f, vb = k + 1 < deg_in ? 1.f : 0.f;
+        const float aa = va * fast_exp2(fminf(ea - dv.y, 100.f)), ab = vb * fast_exp2(fminf(eb - dv.y, 100.f));
+        const float da = aa * fmaf(drop.q(slot0 + (uint32_t)k), ga, -dv.x);
+        const float db = ab * fmaf(drop.q(slot0 + (uint32_t)k + 1u), gb, -dv.x);
+        A_in += da + db;
+        acc_step<C>(B_in, sa, da);
+        acc_step<C>(B_in, sb, db);
+    }
+    // ---- role 2: v as SOURCE, out-edges (v -> u): A_out, B_out, G = sum alpha q g_u ------------------------------
+    const float c1 = cv_dot<C>(attp, xl_v);
+#pragma unroll 1
+    for (int k = 1; k < kmax_out; k += 2) {
+        const ptrdiff_t ua = nbr_out(k), ub = nbr_out(k + 1);
+        CV<C> ra, rb, ga, gb, sa, sb;
+        cv_load<C, VEC>(ra, xr_base + ua * HC, par);
+        cv_load<C, VEC>(rb, xr_base + ub * HC, par);
+        cv_load<C, VEC>(ga, g_base + ua * HC, par);
+        cv_load<C, VEC>(gb, g_base + ub * HC, par);
+        const float2 dua = ds_of(ua, ga), dub = ds_of(ub, gb);
+        const float ea = out_score<C>(attm, c1, xl_v, ra, sa);
+        const float eb = out_score<C>(attm, c1, xl_v, rb, sb);
+        const float gxa = cv_dot<C>(ga, xl_v), gxb = cv_dot<C>(gb, xl_v);
+        const float va = k < deg_out ? 1.f : 0.f, vb = k + 1 < deg_out ? 1.f : 0.f;
+        const float aa = va * fast_exp2(fminf(ea - dua.y, 100.f)), ab = vb * fast_exp2(fminf(eb - dub.y, 100.f));
+        const float qa = drop.q(slot_out(k)), qb = drop.q(slot_out(k + 1));
+        const float da = aa * fmaf(qa, gxa, -dua.x), db = ab * fmaf(qb, gxb, -dub.x);
+        A_out += da + db;
+        acc_step<C>(B_out, sa, da);
+        acc_step<C>(B_out, sb, db);
+        cv_axpy<C>(G, aa * qa, ga);
+        cv_axpy<C>(G, ab * qb, gb);
+    }
+    // ---- rows:  DR = slope A_in + (1-slope) B_in,  d xr = att DR;   DL likewise,  d xl = G + att DL;
+    //      d att partial of this row = xr_v DR + xl_v DL   (lrelu(s) = s lrelu'(s), s = xl + xr) ---------------------
+    const float2 k1 = splat(1.f - slope), ain = splat(slope * A_in), aout = splat(slope * A_out);
 #pragma unroll
-            for (int i = 0; i < CP; ++i) d2 = __ffma2_rn(g_v[i], __fadd2_rn(yv[i], make_float2(-bh[i].x, -bh[i].y)), d2);
-            delta_v = hsum(d2);
-        }
-        const uint32_t key = a.drop_thr ? dropout_snapshot_key(a.seed, (uint32_t)snap) : 0u;
-        const float2 slope2 = make_float2(a.slope, a.slope);
-        const float dslope = 1.f - a.slope;  // lrelu'(s) = slope + (1 - slope) * [s > 0]
-        const float2 dslope2 = make_float2(dslope, dslope);
+    for (int i = 0; i < CV<C>::NP; ++i) {
+        const float2 DR = __ffma2_rn(k1, B_in.p[i], ain), DL = __ffma2_rn(k1, B_out.p[i], aout);
+        dxr.p[i] = __fmul2_rn(att.p[i], DR);
+        dxl.p[i] = __ffma2_rn(att.p[i], DL, G.p[i]);
+        tatt.p[i] = __ffma2_rn(xr_v.p[i], DR, __fmul2_rn(xl_v.p[i], DL));
+    }
+    {
+        const float DR = fmaf(1.f - slope, B_in.s, slope * A_in), DL = fmaf(1.f - slope, B_out.s, slope * A_out);
+        dxr.s = att.s * DR;
+        dxl.s = fmaf(att.s, DL, G.s);
+        tatt.s = fmaf(xr_v.s, DR, xl_v.s * DL);
+    }
+}
 
-        // ---- role 1: v as DESTINATION, in-edges (u -> v): d xr_v, d att ---------------------------------------
-        {
-            const int k1 = __ldg(a.rowptr_in + v + 1);
-            const int k0 = self_only ? k1 - 1 : __ldg(a.rowptr_in + v);
-            const ST *base = xl_w + h * C;
-            for (int k = k0; k < k1; ++k) {
-                const int u = __ldg(a.col_in + k) - lo;
-                float2 xu[CP], s[CP], z[CP];
-                load_row<C>(base + u * HC, xu);
-                const float e = edge_score<C, ST>(att_h, xu, xr_v, slope2, s, z);
-                float2 gx2 = make_float2(0.f, 0.f);
-#pragma unroll
-                for (int i = 0; i < CP; ++i) gx2 = __ffma2_rn(g_v[i], xu[i], gx2);
-                float q = 1.f;
-                if (a.drop_thr) q = dropout_bits16(key, (uint32_t)k, (uint32_t)h) >= a.drop_thr ? a.inv_keep : 0.f;
-                const float alpha = fast_exp2(fmaf(e, kLog2e, -m_v)) * inv_v;
-                const float de = alpha * fmaf(q, hsum(gx2), -delta_v);
-                const float2 de2 = make_float2(de, de);
-#pragma unroll
-                for (int i = 0; i < CP; ++i) {
-                    datt[i] = __ffma2_rn(de2, z[i], datt[i]);
-                    const float2 step = make_float2(s[i].x > 0.f ? 1.f : 0.f, s[i].y > 0.f ? 1.f : 0.f);
-                    const float2 d = __ffma2_rn(step, dslope2, slope2);
-                    dxr[i] = __ffma2_rn(__fmul2_rn(de2, att_h[i]), d, dxr[i]);
-                }
-            }
+template <int C, typename ST, bool VEC>
+__global__ void __launch_bounds__(256, 1) edge_bwd_kernel(const EdgeBwdArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem);
+    uint64_t *empty = full + kMaxStages;
+    uint64_t *yfull = empty + kMaxStages;
+    uint64_t *yempty = yfull + 1;
+    const tg_tile_meta *meta_s = reinterpret_cast<const tg_tile_meta *>(smem + a.off_meta);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ncw = (blockDim.x >> 5) - 1;
+    const int nct = ncw * 32;  // consumer threads
+    const int H = a.H, HC = H * C, T = a.T, N = a.N;
+    const int Ts = (T + 7) & ~7;  // row stride of the slab sections
+    const int NS = a.num_stages;
+    const uint32_t RB_ST = (uint32_t)HC * sizeof(ST), RB_F = (uint32_t)HC * 4u, RB_STAT = (uint32_t)H * 4u;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], ncw);
         }
-        // ---- role 2: v as SOURCE, out-edges (v -> u): d xl_v ---------------------------------------------------
-        {
-            const int k1 = __ldg(a.rowptr_out + v + 1);
-            const int k0 = self_only ? k1 - 1 : __ldg(a.rowptr_out + v);
-            const ST *base_r = xr_w + h * C;
-            const float *base_g = g_w + h * C;
-            for (int k2 = k0; k2 < k1; ++k2) {
-                const int u = __ldg(a.col_out + k2) - lo;
-                float2 xru[CP], gu[CP], s[CP], z[CP];
-                load_row<C>(base_r + u * HC, xru);
-                load_row<C>(base_g + u * HC, gu);
-                const float e = edge_score<C, ST>(att_h, xl_v, xru, slope2, s, z);
-                float2 gx2 = make_float2(0.f, 0.f);
-#pragma unroll
-                for (int i = 0; i < CP; ++i) gx2 = __ffma2_rn(gu[i], xl_v[i], gx2);
-                float m_u, inv_u, delta_u;
-                if (SM) {
-                    m_u = m_s[u * H + h];
-                    inv_u = inv_s[u * H + h];
-                    delta_u = delta_s[u * H + h];
-                } else {
-                    m_u = m_g[u * H + h];
-                    inv_u = 1.f / den_g[u * H + h];
-                    float2 yu[CP], bh[CP], d2 = make_float2(0.f, 0.f);
-                    load_row<C>(y_g + u * HC + h * C, yu);
-                    load_row<C>(a.bias + h * C, bh);
-#pragma unroll
-                    for (int i = 0; i < CP; ++i) d2 = __ffma2_rn(gu[i], __fadd2_rn(yu[i], make_float2(-bh[i].x, -bh[i].y)), d2);
-                    delta_u = hsum(d2);
-                }
-                float q = 1.f;
-                if (a.drop_thr) {
-                    const uint32_t kin = (uint32_t)__ldg(a.slot_out + k2);
-                    q = dropout_bits16(key, kin, (uint32_t)h) >= a.drop_thr ? a.inv_keep : 0.f;
-                }
-                const float alpha = fast_exp2(fmaf(e, kLog2e, -m_u)) * inv_u;
-                const float aq = alpha * q;
-                const float de = alpha * fmaf(q, hsum(gx2), -delta_u);
-                const float2 aq2 = make_float2(aq, aq), de2 = make_float2(de, de);
-#pragma unroll
-                for (int i = 0; i < CP; ++i) {
-                    const float2 step = make_float2(s[i].x > 0.f ? 1.f : 0.f, s[i].y > 0.f ? 1.f : 0.f);
-                    const float2 d = __ffma2_rn(step, dslope2, slope2);
-                    dxl[i] = __ffma2_rn(__fmul2_rn(de2, att_h[i]), d, __ffma2_rn(aq2, gu[i], dxl[i]));
-                }
-            }
-        }
+        mbar_init(yfull, 1);
+        mbar_init(yempty, ncw);
+        fence_mbar_init();
     }
-
-    // ---- d bias partial straight from the g tile (before any region is recycled) ------------------------
-    float dbias_j = 0.f;
-    if (tid < HC) {
-        const float *gp = g_w + (n0 - lo) * HC + tid;
-        for (int r = 0; r < nt; ++r) dbias_j += gp[r * HC];
-    }
-    __syncthreads();  // every lane is done reading the windows: recycle xl/xr regions as output staging
-    ST *dxl_s = reinterpret_cast<ST *>(xl_base);
-    ST *dxr_s = reinterpret_cast<ST *>(xr_base);
-    float *red = reinterpret_cast<float *>(y_base);  // (C, nt*H) d att scratch
-    const int ntl = nt * H;
-    if (active) {
-        store_row<C>(dxl_s + node_l * HC + h * C, dxl);
-        store_row<C>(dxr_s + node_l * HC + h * C, dxr);
-#pragma unroll
-        for (int c = 0; c < C; ++c) red[c * ntl + tid] = (c & 1) ? datt[c / 2].y : datt[c / 2].x;
-    }
+    if (a.num_tiles <= kMetaSmemTiles)
+        for (int i = threadIdx.x; i < a.num_tiles * 8; i += blockDim.x)
+            reinterpret_cast<int32_t *>(smem + a.off_meta)[i] = reinterpret_cast<const int32_t *>(a.meta)[i];
     __syncthreads();
-    ST *dxl_g = static_cast<ST *>(a.dxl) + (static_cast<int64_t>(snap) * a.N + n0) * HC;
-    ST *dxr_g = static_cast<ST *>(a.dxr) + (static_cast<int64_t>(snap) * a.N + n0) * HC;
-    for (int i = tid; i < nt * HC; i += blockDim.x) {
-        dxl_g[i] = dxl_s[i];
-        dxr_g[i] = dxr_s[i];
-    }
-    if (tid < HC) {
-        const int hh = tid / C, c = tid - hh * C;
-        const float *rp = red + c * ntl + hh;
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;  // fixed order: deterministic
-        int n = 0;
-        for (; n + 4 <= nt; n += 4) {
-            s0 += rp[(n + 0) * H];
-            s1 += rp[(n + 1) * H];
-            s2 += rp[(n + 2) * H];
-            s3 += rp[(n + 3) * H];
+    const ItemRange R = cta_items(a.items);
+    int snap = (int)(R.w0 / a.num_tiles), tile = (int)(R.w0 % a.num_tiles);
+    const int64_t Rtot = (int64_t)a.S * N;
+    Ring ring{0, 0u};
+    uint32_t yph = 0;  // phase parity of the single y window
+
+    if (warp == ncw) {
+        // ================================ producer warp ================================
+        for (int64_t w = R.w0; w < R.w1; ++w) {
+            const tg_tile_meta m = load_meta(meta_s, a.meta, a.num_tiles, tile);
+            const int n0 = tile * T, nt = min(N, n0 + T) - n0;
+            const bool lit = a.literal && snap > 0;
+            const int lo = lit ? n0 : m.lo, win = lit ? nt : m.hi - m.lo;
+            const bool staged = m.eligible && win <= a.cap_rows && (m.kin_kout & 0xFFFF) <= a.cap_kin && (m.kin_kout >> 16) <= a.cap_kout;
+            if (staged) {
+                const int64_t row0 = (int64_t)snap * N + lo;
+                unsigned char *stage = smem + a.off_stage0 + (size_t)ring.st * a.stage_bytes;
+                const WinCopy c0 = win_copy(a.xl, row0, win, RB_ST, a.per_st, Rtot);
+                const WinCopy c1 = win_copy(a.xr, row0, win, RB_ST, a.per_st, Rtot);
+                const WinCopy c2 = win_copy(a.gy, row0, win, RB_F, a.per_f, Rtot);
+                const WinCopy c3 = win_copy(a.stat, row0, win, RB_STAT, a.per_stat, Rtot);
+                const WinCopy c4 = win_copy(a.y, row0, win, RB_F, a.per_f, Rtot);
+                if (lane == 0) mbar_wait(&empty[ring.st], ring.ph ^ 1u);
+                __syncwarp();
+                if (c0.tail | c1.tail | c2.tail | c3.tail) {  // only the last rows of the last snapshot
+                    win_copy_tail(c0, stage + a.off_xl, lane);
+                    win_copy_tail(c1, stage + a.off_xr, lane);
+                    win_copy_tail(c2, stage + a.off_g, lane);
+                    win_copy_tail(c3, stage + a.off_statraw, lane);
+                    __syncwarp();
+                }
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(&full[ring.st], (uint32_t)m.slab_bytes + c0.mid + c1.mid + c2.mid + c3.mid);
+                    bulk_g2s(stage, a.slabs + m.slab_off, (uint32_t)m.slab_bytes, &full[ring.st]);
+                    if (c0.mid) bulk_g2s(stage + a.off_xl, c0.src, c0.mid, &full[ring.st]);
+                    if (c1.mid) bulk_g2s(stage + a.off_xr, c1.src, c1.mid, &full[ring.st]);
+                    if (c2.mid) bulk_g2s(stage + a.off_g, c2.src, c2.mid, &full[ring.st]);
+                    if (c3.mid) bulk_g2s(stage + a.off_statraw, c3.src, c3.mid, &full[ring.st]);
+                    mbar_wait(yempty, yph ^ 1u);  // the single y window: released right after the delta pre-pass
+                }
+                __syncwarp();
+                if (c4.tail) {
+                    win_copy_tail(c4, smem + a.off_y, lane);
+                    __syncwarp();
+                }
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(yfull, c4.mid);
+                    if (c4.mid) bulk_g2s(smem + a.off_y, c4.src, c4.mid, yfull);
+                }
+                ring.advance(NS);
+                yph ^= 1u;
+            }
+            if (++tile == a.num_tiles) { tile = 0; ++snap; }
         }
-        for (; n < nt; ++n) s0 += rp[n * H];
-        float *out = a.partials + static_cast<int64_t>(blockIdx.x) * 2 * HC;
-        out[tid] = (s0 + s1) + (s2 + s3);
-        out[HC + tid] = dbias_j;
+        return;
+    }
+
+    // ================================ consumer warps ================================
+    const int npw = a.npw;
+    const int nw = lane & (npw - 1);
+    const int h = lane / npw;
+    const int node_l = warp * npw + nw;
+    const bool head_ok = h < H;
+    const int hh = head_ok ? h : 0;
+    const int par = VEC ? ((hh * C) & 1) : 0;
+    const int ctid = threadIdx.x;  // consumer thread id (consumer warps come first)
+    CV<C> attp, attm, att_h, bias_h;
+    cv_load_param<C>(attp, a.att + hh * C, par, 0.5f * (1.f + a.slope) * kLog2e);
+    cv_load_param<C>(attm, a.att + hh * C, par, 0.5f * (1.f - a.slope) * kLog2e);
+    cv_load_param<C>(att_h, a.att + hh * C, par, 1.f);
+    cv_load_param<C>(bias_h, a.bias + hh * C, par, 1.f);
+    const uint32_t head_key = dropout_head_key((uint32_t)hh);
+    uint32_t key = 0;
+    int key_snap = -1;
+    // persistent fp64 partial sums of d att and d bias for this lane's (head, channel arrangement)
+    double datt_p[CV<C>::NP > 0 ? CV<C>::NP : 1][2], datt_s = 0.0, dbias_p[CV<C>::NP > 0 ? CV<C>::NP : 1][2], dbias_s = 0.0;
+#pragma unroll
+    for (int i = 0; i < CV<C>::NP; ++i) datt_p[i][0] = datt_p[i][1] = dbias_p[i][0] = dbias_p[i][1] = 0.0;
+    ST *out_l = reinterpret_cast<ST *>(smem + a.off_out) + warp * npw * HC;               // d xl rows of this warp
+    ST *out_r = reinterpret_cast<ST *>(smem + a.off_out) + (size_t)T * HC + warp * npw * HC;  // d xr rows
+
+    for (int64_t w = R.w0; w < R.w1; ++w) {
+        const tg_tile_meta m = load_meta(meta_s, a.meta, a.num_tiles, tile);
+        const int n0 = tile * T, nt = min(N, n0 + T) - n0;
+        const bool lit = a.literal && snap > 0;
+        const int lo = lit ? n0 : m.lo, win = lit ? nt : m.hi - m.lo;
+        const bool staged = m.eligible && win <= a.cap_rows && (m.kin_kout & 0xFFFF) <= a.cap_kin && (m.kin_kout >> 16) <= a.cap_kout;
+        const bool active = head_ok && node_l < nt;
+        const int64_t row = (int64_t)snap * N + n0 + node_l;
+        if (a.drop_thr && snap != key_snap) {
+            key = dropout_snapshot_key(a.seed, (uint32_t)snap) ^ head_key;
+            key_snap = snap;
+        }
+        DropCfg drop;
+        drop.thr = a.drop_thr;
+        drop.key = key;
+        drop.inv_keep = a.inv_keep;
+        CV<C> dxl, dxr, tatt, g_v;
+        if (staged) {
+            const int64_t row0 = (int64_t)snap * N + lo;
+            unsigned char *stage = smem + a.off_stage0 + (size_t)ring.st * a.stage_bytes;
+            const int32_t *hdr = reinterpret_cast<const int32_t *>(stage);
+            const int32_t *k0s = hdr + 4;
+            const int32_t *degs = k0s + Ts;
+            const int kin_t = m.kin_kout & 0xFFFF, kout_t = m.kin_kout >> 16;
+            const uint16_t *ell_in = reinterpret_cast<const uint16_t *>(degs + Ts) + node_l;
+            const uint16_t *ell_out = ell_in + (size_t)kin_t * Ts;
+            const uint16_t *slot_rel = ell_out + (size_t)kout_t * Ts;
+            const ST *xl_s = reinterpret_cast<const ST *>(stage + a.off_xl + win_skip(row0, RB_ST, a.per_st));
+            const ST *xr_s = reinterpret_cast<const ST *>(stage + a.off_xr + win_skip(row0, RB_ST, a.per_st));
+            const float *g_s = reinterpret_cast<const float *>(stage + a.off_g + win_skip(row0, RB_F, a.per_f));
+            const float *stat_s = reinterpret_cast<const float *>(stage + a.off_statraw + win_skip(row0, RB_STAT, a.per_stat));
+            const float *y_s = reinterpret_cast<const float *>(smem + a.off_y + win_skip(row0, RB_F, a.per_f));
+            float2 *ds = reinterpret_cast<float2 *>(stage + a.off_ds);  // [head][window row] -> (delta, stat)
+            mbar_wait(&full[ring.st], ring.ph);
+            mbar_wait(yfull, yph);
+            // ---- pre-pass: delta = g . (y - bias) for the window rows of this lane's head (rows node_l, node_l + T, ..)
+            if (head_ok) {
+                for (int r = node_l; r < win; r += T) {
+                    CV<C> gg, yy;
+                    cv_load<C, VEC>(gg, g_s + r * HC + hh * C, par);
+                    cv_load<C, VEC>(yy, y_s + r * HC + hh * C, par);
+                    float2 d2 = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int q = 0; q < CV<C>::NP; ++q) d2 = __ffma2_rn(gg.p[q], __fadd2_rn(yy.p[q], make_float2(-bias_h.p[q].x, -bias_h.p[q].y)), d2);
+                    float dl = d2.x + d2.y;
+                    if (CV<C>::ODD) dl = fmaf(gg.s, yy.s - bias_h.s, dl);
+                    ds[hh * a.cap_rows + r] = make_float2(dl, stat_s[r * H + hh]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(yempty);  // y window may be refilled for the next item
+            yph ^= 1u;
+            bar_sync_named(kBarConsumers, nct);  // delta of every window row is visible to every consumer warp
+
+            const int vl = n0 + node_l - lo;  // own row inside the window
+            int deg_in = 0, deg_out = 0;
+            uint32_t slot0 = 0;
+            if (active) {
+                const int d = degs[node_l];
+                deg_in = d & 0xFFFF;
+                deg_out = d >> 16;
+                if (lit) { deg_in = min(deg_in, 1); deg_out = min(deg_out, 1); }
+                slot0 = (uint32_t)k0s[node_l];
+            }
+            const uint32_t slot_base = (uint32_t)hdr[3];
+            const float2 *ds_h = ds + hh * a.cap_rows;
+            const float2 dv = active ? ds_h[vl] : make_float2(0.f, 0.f);
+            const int kmax_in = __reduce_max_sync(0xFFFFFFFFu, deg_in), kmax_out = __reduce_max_sync(0xFFFFFFFFu, deg_out);
+            bwd_lane<C, ST, VEC>(
+                attp, attm, att_h, a.slope, drop, xl_s + hh * C, xr_s + hh * C, g_s + hh * C, HC, par, (ptrdiff_t)vl, dv, deg_in, kmax_in,
+                deg_out, kmax_out, slot0, [&](int k) -> ptrdiff_t { return (ptrdiff_t)ell_in[k * Ts]; },
+                [&](int k) -> ptrdiff_t { return (ptrdiff_t)ell_out[k * Ts]; },
+                [&](int k) -> uint32_t { return slot_base + (uint32_t)slot_rel[k * Ts]; },
+                [&](ptrdiff_t u, const CV<C> &) -> float2 { return ds_h[u]; }, active, dxl, dxr, tatt, g_v);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[ring.st]);
+            ring.advance(NS);
+            // ---- outputs: stage the warp's rows, write them as contiguous runs -----------------------------------
+            if (active) {
+                cv_store<C, VEC>(out_l + nw * HC + hh * C, dxl, par);
+                cv_store<C, VEC>(out_r + nw * HC + hh * C, dxr, par);
+            }
+            __syncwarp();
+            const int nv = max(0, min(npw, nt - warp * npw));
+            const int64_t r0 = ((int64_t)snap * N + n0 + warp * npw) * HC;
+            ST *dl_g = static_cast<ST *>(a.dxl) + r0, *dr_g = static_cast<ST *>(a.dxr) + r0;
+            if (VEC) {  // rows are pair aligned (8 B fp32 / 4 B bf16) in shared and in global memory
+                using W = typename std::conditional<sizeof(ST) == 4, uint2, uint32_t>::type;
+                const W *sl = reinterpret_cast<const W *>(out_l), *sr = reinterpret_cast<const W *>(out_r);
+                for (int i = lane; i < nv * HC / 2; i += 32) {
+                    reinterpret_cast<W *>(dl_g)[i] = sl[i];
+                    reinterpret_cast<W *>(dr_g)[i] = sr[i];
+                }
+            } else {
+                for (int i = lane; i < nv * HC; i += 32) {
+                    dl_g[i] = out_l[i];
+                    dr_g[i] = out_r[i];
+                }
+            }
+            __syncwarp();
+        } else {
+            // ---- window too large for a stage: everything straight from global memory (L2) --------------------------
+            const int64_t snap0 = (int64_t)snap * N;
+            const ST *xl_snap = static_cast<const ST *>(a.xl) + snap0 * HC + hh * C;
+            const ST *xr_snap = static_cast<const ST *>(a.xr) + snap0 * HC + hh * C;
+            const float *g_snap = a.gy + snap0 * HC + hh * C;
+            const float *y_snap = a.y + snap0 * HC + hh * C;
+            const float *stat_snap = a.stat + snap0 * H + hh;
+            auto ds_of = [&](ptrdiff_t node, const CV<C> &gn) -> float2 {
+                CV<C> yy;
+                cv_load<C, VEC>(yy, y_snap + node * HC, par);
+                float2 d2 = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int q = 0; q < CV<C>::NP; ++q) d2 = __ffma2_rn(gn.p[q], __fadd2_rn(yy.p[q], make_float2(-bias_h.p[q].x, -bias_h.p[q].y)), d2);
+                float dl = d2.x + d2.y;
+                if (CV<C>::ODD) dl = fmaf(gn.s, yy.s - bias_h.s, dl);
+                return make_float2(dl, stat_snap[node * H]);
+            };
+            const int v = n0 + node_l;
+            int k0i = 0, deg_in = 0, k0o = 0, deg_out = 0;
+            float2 dv = make_float2(0.f, 0.f);
+            if (active) {
+                k0i = __ldg(a.rowptr_in + v);
+                deg_in = __ldg(a.rowptr_in + v + 1) - k0i;
+                k0o = __ldg(a.rowptr_out + v);
+                deg_out = __ldg(a.rowptr_out + v + 1) - k0o;
+                if (lit) { deg_in = min(deg_in, 1); deg_out = min(deg_out, 1); }
+                CV<C> gv0;
+                cv_load<C, VEC>(gv0, g_snap + (ptrdiff_t)v * HC, par);
+                dv = ds_of(v, gv0);
+            }
+            const int kmax_in = __reduce_max_sync(0xFFFFFFFFu, deg_in), kmax_out = __reduce_max_sync(0xFFFFFFFFu, deg_out);
+            const int vsafe = active ? v : 0;
+            bwd_lane<C, ST, VEC>(
+                attp, attm, att_h, a.slope, drop, xl_snap, xr_snap, g_snap, HC, par, (ptrdiff_t)vsafe, dv, deg_in, kmax_in, deg_out, kmax_out,
+                (uint32_t)k0i, [&](int k) -> ptrdiff_t { return k < deg_in ? (ptrdiff_t)__ldg(a.col_in + k0i + k) : (ptrdiff_t)vsafe; },
+                [&](int k) -> ptrdiff_t { return k < deg_out ? (ptrdiff_t)__ldg(a.col_out + k0o + k) : (ptrdiff_t)vsafe; },
+                [&](int k) -> uint32_t { return k < deg_out ? (uint32_t)__ldg(a.slot_out + k0o + k) : 0u; }, ds_of, active, dxl, dxr, tatt,
+                g_v);
+            if (active) {
+                cv_store<C, VEC>(static_cast<ST *>(a.dxl) + row * HC + hh * C, dxl, par);
+                cv_store<C, VEC>(static_cast<ST *>(a.dxr) + row * HC + hh * C, dxr, par);
+            }
+        }
+        // ---- parameter-gradient partials of this item (fp64 across items) ------------------------------------------
+        if (active) {
+#pragma unroll
+            for (int i = 0; i < CV<C>::NP; ++i) {
+                datt_p[i][0] += (double)tatt.p[i].x;
+                datt_p[i][1] += (double)tatt.p[i].y;
+                dbias_p[i][0] += (double)g_v.p[i].x;
+                dbias_p[i][1] += (double)g_v.p[i].y;
+            }
+            if (CV<C>::ODD) {
+                datt_s += (double)tatt.s;
+                dbias_s += (double)g_v.s;
+            }
+        }
+        if (++tile == a.num_tiles) { tile = 0; ++snap; }
+    }
+
+    // ---- CTA partial of d att / d bias: fixed-order reduction over the lanes of a head, then over the warps -------------
+    bar_sync_named(kBarConsumers, nct);  // every consumer warp is done with the rings: reuse the y window as scratch
+    double *scratch = reinterpret_cast<double *>(smem + a.off_y);  // (ncw, H, 2, C) doubles
+    {
+        auto put = [&](int which, int c, double v) {
+            // sum over the npw lanes of this head inside the warp (xor-shuffle tree: fixed order)
+            for (int off = npw >> 1; off > 0; off >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, off);
+            if (nw == 0 && head_ok) scratch[((warp * H + hh) * 2 + which) * C + c] = v;
+        };
+#pragma unroll
+        for (int i = 0; i < CV<C>::NP; ++i) {
+            put(0, 2 * i + par, datt_p[i][0]);
+            put(0, 2 * i + 1 + par, datt_p[i][1]);
+            put(1, 2 * i + par, dbias_p[i][0]);
+            put(1, 2 * i + 1 + par, dbias_p[i][1]);
+        }
+        if (CV<C>::ODD) {
+            put(0, par ? 0 : C - 1, datt_s);
+            put(1, par ? 0 : C - 1, dbias_s);
+        }
+    }
+    bar_sync_named(kBarConsumers, nct);
+    if (ctid < 2 * HC) {
+        const int which = ctid / HC, j = ctid - which * HC, hd = j / C, c = j - hd * C;
+        double v = 0.0;
+        for (int wq = 0; wq < ncw; ++wq) v += scratch[((wq * H + hd) * 2 + which) * C + c];
+        a.partials[(int64_t)blockIdx.x * 2 * HC + which * HC + j] = (float)v;
     }
 }
 
-template <int C, typename ST>
-__global__ void __launch_bounds__(256, 2) edge_bwd_kernel(const EdgeBwdArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int tile = blockIdx.x % a.num_tiles;
-    const int snap = blockIdx.x / a.num_tiles;
-    int win = a.tile_hi[tile] - a.tile_lo[tile];
-    if (a.literal && snap > 0) win = min(a.N, (tile + 1) * a.T) - tile * a.T;
-    if (win <= a.win_rows_smem)
-        edge_bwd_body<C, ST, true>(a, smem_raw);
-    else
-        edge_bwd_body<C, ST, false>(a, smem_raw);
+struct StagePickBwd {
+    int num_stages, cap_rows, cap_kin, cap_kout;
+    uint32_t stage_bytes, off_statraw, off_ds, off_xl, off_xr, off_g;
+};
+struct BwdGeom {  // everything the stage sizes depend on
+    int T, H, HC;
+    size_t es;
+    int per_st, per_f, per_stat;
+    size_t slab(int kin, int kout) const { return size_t(round16(16 + 8 * ((T + 7) & ~7) + 2 * ((T + 7) & ~7) * (kin + 2 * kout))); }
+    size_t win_st(int rows) const { return round16(uint32_t((rows + 2 * (per_st - 1)) * HC * es)); }
+    size_t win_f(int rows) const { return round16(uint32_t((rows + 2 * (per_f - 1)) * HC * 4)); }
+    size_t win_stat(int rows) const { return round16(uint32_t((rows + 2 * (per_stat - 1)) * H * 4)); }
+    size_t ds(int rows) const { return round16(uint32_t(rows * H * 8)); }
+    size_t stage(int rows, int kin, int kout) const { return slab(kin, kout) + win_stat(rows) + ds(rows) + 2 * win_st(rows) + win_f(rows); }
+};
+static StagePickBwd pick_stages_bwd(const tg_tiling &tl, const BwdGeom &g, size_t fixed_bytes, int want_stages) {
+    StagePickBwd best{0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    double best_score = -1.0;
+    for (int ns = want_stages; ns >= 1; --ns) {
+        int cap_rows = 0, kin = 0, kout = 0, staged = 0;
+        std::vector<std::pair<size_t, int>> need;
+        for (int t = 0; t < tl.num_tiles; ++t) {
+            const tg_tile_meta &m = tl.h_meta[t];
+            if (m.eligible) need.push_back({g.stage(m.hi - m.lo, m.kin_kout & 0xFFFF, m.kin_kout >> 16), t});
+        }
+        std::sort(need.begin(), need.end());
+        for (auto &nt : need) {
+            const tg_tile_meta &m = tl.h_meta[nt.second];
+            const int r = std::max(cap_rows, std::max(m.hi - m.lo, g.T)), ki = std::max(kin, m.kin_kout & 0xFFFF), ko = std::max(kout, m.kin_kout >> 16);
+            const size_t total = fixed_bytes + g.win_f(r) /* the single y window */ + ns * g.stage(r, ki, ko) + 256;
+            if (total > size_t(kEdgeSmemBudget)) break;
+            cap_rows = r; kin = ki; kout = ko;
+            ++staged;
+        }
+        if (!staged) continue;
+        const double frac = double(staged) / tl.num_tiles;
+        const double score = frac * (ns >= 2 ? 1.0 : 0.6);
+        if (score > best_score) {
+            best_score = score;
+            best.num_stages = ns;
+            best.cap_rows = cap_rows;
+            best.cap_kin = kin;
+            best.cap_kout = kout;
+            best.off_statraw = (uint32_t)g.slab(kin, kout);
+            best.off_ds = best.off_statraw + (uint32_t)g.win_stat(cap_rows);
+            best.off_xl = best.off_ds + (uint32_t)g.ds(cap_rows);
+            best.off_xr = best.off_xl + (uint32_t)g.win_st(cap_rows);
+            best.off_g = best.off_xr + (uint32_t)g.win_st(cap_rows);
+            best.stage_bytes = (uint32_t)g.stage(cap_rows, kin, kout);
+        }
+        if (frac >= 0.9) break;
+    }
+    return best;
 }
 
-template <int C, typename ST>
-static int launch_bwd(const EdgeBwdArgs &a, int threads, int max_win, cudaStream_t st) {
-    EdgeBwdArgs b = a;
-    const int H = a.H, HC = H * C;
-    // bytes per window row across the four regions and the three stat arrays
-    const size_t per_row = size_t(HC) * (2 * sizeof(ST) + 2 * sizeof(float)) + size_t(H) * 12;
-    const size_t fixed = 16 + 4 * 32 + 64;
-    int rows_fit = int((size_t(kSmemBudget) - fixed) / per_row);
-    if (rows_fit < a.T) {
-        tecgat_set_error("edge_bwd: a tile of %d nodes x %d channels does not fit shared memory", a.T, HC);
-        return TECGAT_ENOSUP;
-    }
-    b.win_rows_smem = rows_fit < max_win ? rows_fit : max_win;
-    b.region_rows = b.win_rows_smem > a.T ? b.win_rows_smem : a.T;
-    const size_t smem = 16 + 2 * (round16(uint32_t(b.region_rows * HC * sizeof(ST))) + 16) +
-                        2 * (round16(uint32_t(b.region_rows * HC * sizeof(float))) + 16) + size_t(b.region_rows) * H * 12 + 16;
-    auto kern = edge_bwd_kernel<C, ST>;
+template <int C, typename ST, bool VEC>
+static int launch_bwd(EdgeBwdArgs a, const tecgat_plan_t *plan, int grid, cudaStream_t st) {
+    const tg_tiling &tl = plan->bwd;
+    const int H = a.H, HC = H * C, T = tl.T;
+    const int hp = pad_heads(H);
+    a.npw = 32 / hp;
+    const int ncw = T / a.npw;
+    BwdGeom g{T, H, HC, sizeof(ST), row_period(uint32_t(HC * sizeof(ST))), row_period(uint32_t(HC * 4)), row_period(uint32_t(H * 4))};
+    a.per_st = g.per_st; a.per_f = g.per_f; a.per_stat = g.per_stat;
+    const size_t out_bytes = (2 * size_t(T) * HC * sizeof(ST) + 15) & ~size_t(15);
+    const size_t scratch_bytes = size_t(ncw) * H * 2 * C * sizeof(double);  // end-of-kernel reduction, aliases the y window
+    const size_t meta_bytes = tl.num_tiles <= kMetaSmemTiles ? size_t(tl.num_tiles) * 32 : 0;
+    const size_t fixed = 128 + meta_bytes + out_bytes;
+    const char *env = getenv("TECGAT_BWD_STAGES");
+    const int want = env ? std::max(1, std::min(kMaxStages, atoi(env))) : 2;
+    const StagePickBwd sp = pick_stages_bwd(tl, g, fixed, want);
+    a.num_stages = sp.num_stages > 0 ? sp.num_stages : 1;
+    a.cap_rows = sp.cap_rows;
+    a.cap_kin = sp.num_stages > 0 ? sp.cap_kin : -1;
+    a.cap_kout = sp.cap_kout;
+    size_t ybytes = g.win_f(a.cap_rows);
+    if (ybytes < scratch_bytes) ybytes = (scratch_bytes + 15) & ~size_t(15);
+    a.off_meta = 128;
+    a.off_y = (uint32_t)(128 + meta_bytes);
+    a.off_out = (uint32_t)(a.off_y + ybytes);
+    a.off_stage0 = (uint32_t)((a.off_out + out_bytes + 127) & ~size_t(127));
+    a.stage_bytes = sp.stage_bytes;
+    a.off_statraw = sp.off_statraw; a.off_ds = sp.off_ds; a.off_xl = sp.off_xl; a.off_xr = sp.off_xr; a.off_g = sp.off_g;
+    const size_t smem = a.off_stage0 + size_t(sp.num_stages) * a.stage_bytes;
+    TG_REQUIRE(smem <= 227 * 1024, TECGAT_ENOSUP, "edge_bwd: %zu B shared memory needed (tile %d x %d channels)", smem, T, HC);
+    auto kern = edge_bwd_kernel<C, ST, VEC>;
     TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t grid = int64_t(a.num_tiles) * a.S;
-    kern<<<(unsigned)grid, threads, smem, st>>>(b);
+    kern<<<(unsigned)grid, (ncw + 1) * 32, smem, st>>>(a);
     TG_LAUNCH_CHECK();
     return TECGAT_OK;
+}
+
+static int bwd_grid(const tecgat_plan_t *plan, int32_t snapshots) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t items = int64_t(plan->bwd.num_tiles) * snapshots;
+    return (int)std::min<int64_t>(items, sms);
 }
 
 }  // namespace tg
@@ -304,48 +595,55 @@ static int launch_bwd(const EdgeBwdArgs &a, int threads, int max_win, cudaStream
 extern "C" int64_t tecgat_edge_bwd_workspace(const tecgat_plan_t *plan, int32_t snapshots, int32_t heads,
                                              int32_t out_channels) {
     if (!plan || snapshots <= 0 || heads <= 0 || out_channels <= 0) return 0;
-    return int64_t(plan->num_tiles) * snapshots * 2 * heads * out_channels * (int64_t)sizeof(float);
+    return int64_t(tg::bwd_grid(plan, snapshots)) * 2 * heads * out_channels * (int64_t)sizeof(float);
 }
 
 extern "C" int tecgat_edge_bwd(const tecgat_plan_t *plan, const void *xl, const void *xr, const float *att,
-                               const float *bias, const float *y, const float *m, const float *den, const float *gy,
-                               void *dxl, void *dxr, float *datt, float *dbias, void *workspace, int32_t snapshots,
-                               int32_t heads, int32_t out_channels, float negative_slope, float dropout_p, uint64_t seed,
-                               int32_t mode, int32_t dtype, void *stream) {
+                               const float *bias, const float *y, const float *stat, const float *gy, void *dxl,
+                               void *dxr, float *datt, float *dbias, void *workspace, int32_t snapshots, int32_t heads,
+                               int32_t out_channels, float negative_slope, float dropout_p, uint64_t seed, int32_t mode,
+                               int32_t dtype, void *stream) {
     using namespace tg;
-    TG_REQUIRE(plan && xl && xr && att && bias && y && m && den && gy && dxl && dxr && datt && dbias && workspace,
+    TG_REQUIRE(plan && xl && xr && att && bias && y && stat && gy && dxl && dxr && datt && dbias && workspace,
                TECGAT_EINVAL, "edge_bwd: NULL argument");
     TG_REQUIRE(snapshots > 0 && heads > 0 && out_channels > 0, TECGAT_EINVAL, "edge_bwd: non-positive size");
+    TG_REQUIRE(heads <= 32, TECGAT_ENOSUP, "edge_bwd: heads %d > 32", heads);
     TG_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, TECGAT_EINVAL, "edge_bwd: dropout_p %f outside [0, 1)", dropout_p);
-    TG_REQUIRE(negative_slope >= 0.f && negative_slope <= 1.f, TECGAT_ENOSUP, "edge_bwd: negative_slope %f outside [0, 1]", negative_slope);
     TG_REQUIRE(mode == TECGAT_MODE_SHARED || mode == TECGAT_MODE_LITERAL, TECGAT_EINVAL, "edge_bwd: bad mode %d", mode);
     TG_REQUIRE(dtype == TECGAT_F32 || dtype == TECGAT_BF16, TECGAT_EINVAL, "edge_bwd: bad dtype %d", dtype);
-    const int threads = ((plan->tile_nodes * heads + 31) / 32) * 32;
-    TG_REQUIRE(threads <= 256, TECGAT_ENOSUP, "edge_bwd: tile_nodes (%d) * heads (%d) exceeds 256 lanes", plan->tile_nodes, heads);
+    const int hp = pad_heads(heads);
+    const tg_tiling &tl = plan->bwd;
+    TG_REQUIRE(tl.T % (32 / hp) == 0 && tl.T * hp <= 224, TECGAT_ENOSUP,
+               "edge_bwd: backward tile of %d nodes x %d heads does not map onto <= 7 consumer warps; build the plan with "
+               "tile_nodes_bwd = a multiple of %d and <= %d", tl.T, heads, 32 / hp, 224 / hp);
     const int HC = heads * out_channels;
-    TG_REQUIRE(HC <= threads, TECGAT_ENOSUP, "edge_bwd: heads*out_channels (%d) exceeds the CTA size (%d)", HC, threads);
-    const int64_t grid = int64_t(plan->num_tiles) * snapshots;
-    TG_REQUIRE(grid < (int64_t(1) << 31), TECGAT_ENOSUP, "edge_bwd: grid too large");
+    TG_REQUIRE(2 * HC <= tl.T * hp, TECGAT_ENOSUP, "edge_bwd: 2*heads*out_channels (%d) exceeds the consumer threads (%d)", 2 * HC, tl.T * hp);
+    const bool vec = (HC % 2) == 0;
+    {
+        auto al = [](const void *p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
+        TG_REQUIRE(al(xl) && al(xr) && al(dxl) && al(dxr) && al(y) && al(gy) && al(stat), TECGAT_EINVAL,
+                   "edge_bwd: xl / xr / dxl / dxr / y / gy / stat must be 16-byte aligned");
+    }
     EdgeBwdArgs a;
-    a.xl = xl; a.xr = xr; a.att = att; a.bias = bias; a.y = y; a.m = m; a.den = den; a.gy = gy;
+    a.xl = xl; a.xr = xr; a.att = att; a.bias = bias; a.y = y; a.stat = stat; a.gy = gy;
     a.dxl = dxl; a.dxr = dxr; a.partials = static_cast<float *>(workspace);
+    a.meta = tl.meta; a.slabs = tl.slabs;
     a.rowptr_in = plan->rowptr_in; a.col_in = plan->col_in; a.rowptr_out = plan->rowptr_out; a.col_out = plan->col_out;
-    a.slot_out = plan->slot_out; a.tile_lo = plan->tile_lo; a.tile_hi = plan->tile_hi;
-    a.N = plan->num_nodes; a.T = plan->tile_nodes; a.num_tiles = plan->num_tiles; a.S = snapshots; a.H = heads;
-    a.E = plan->num_edges;
+    a.slot_out = plan->slot_out;
+    a.N = plan->num_nodes; a.T = tl.T; a.num_tiles = tl.num_tiles; a.S = snapshots; a.H = heads; a.npw = 0;
     a.slope = negative_slope;
-    a.drop_thr = dropout_p > 0.f ? dropout_threshold(dropout_p) : 0u;
+    a.drop_thr = dropout_p > 0.f ? std::max(1u, dropout_threshold(dropout_p)) : 0u;
     a.inv_keep = 1.f / (1.f - dropout_p);
     a.seed = seed;
     a.literal = (mode == TECGAT_MODE_LITERAL);
-    a.win_rows_smem = 0;
-    a.region_rows = 0;
+    a.items = int64_t(tl.num_tiles) * snapshots;
+    const int grid = bwd_grid(plan, snapshots);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int rc = TECGAT_ENOSUP;
-#define TG_CASE(CC)                                                                                  \
-    case CC:                                                                                         \
-        rc = dtype == TECGAT_F32 ? launch_bwd<CC, float>(a, threads, plan->max_window, st)           \
-                                 : launch_bwd<CC, __nv_bfloat16>(a, threads, plan->max_window, st);  \
+#define TG_CASE(CC)                                                                                                          \
+    case CC:                                                                                                                 \
+        if (vec) rc = dtype == TECGAT_F32 ? launch_bwd<CC, float, true>(a, plan, grid, st) : launch_bwd<CC, __nv_bfloat16, true>(a, plan, grid, st); \
+        else if constexpr ((CC % 2) == 1) rc = dtype == TECGAT_F32 ? launch_bwd<CC, float, false>(a, plan, grid, st) : launch_bwd<CC, __nv_bfloat16, false>(a, plan, grid, st); \
         break;
     switch (out_channels) {
         TG_FOR_EACH_C(TG_CASE)

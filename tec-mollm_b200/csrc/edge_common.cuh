@@ -1,21 +1,24 @@
-// edge_common.cuh -- pieces shared by the fused edge forward / backward kernels.
+// edge_common.cuh -- machinery shared by the fused edge forward / backward kernels (edge_fwd.cu, edge_bwd.cu).
 //
-// Work decomposition (both kernels): one CTA = (tile of `T` consecutive destination nodes, one snapshot).
-// Because the graph is identical across snapshots, the CSR, the tile windows and the parameters are the same
-// for every CTA column; only the row slab changes.  Inside a CTA one LANE owns one (node, head) pair -- thread
-// id = node_local * H + head -- so that a lane's C channels sit at shared-memory word stride C across lanes
-// (C = 11: conflict-free), and the per-destination softmax needs no cross-lane traffic at all.
+// Execution model (both kernels): PERSISTENT, warp-specialised CTAs, one per SM.  The work list is every
+// (snapshot, tile-of-T-destination-nodes) item in snapshot-major order; CTA c owns the contiguous slice
+// [c W / G, (c+1) W / G) so consecutive items of a CTA are neighbouring tiles of one snapshot and their overlapping
+// row windows are re-read from L2, not HBM.  One PRODUCER warp streams each item's inputs -- the tile's ELL slab
+// (plan.cu), the tile's own rows and the contiguous window of neighbour rows -- into a ring of shared-memory stages
+// with bulk-TMA copies (cp.async.bulk, mbarrier complete_tx); the CONSUMER warps compute out of shared memory and
+// hand the stage back through a second mbarrier.  No __syncthreads after set-up: warps drift freely.
 //
-// The rows a tile touches (its nodes plus all their in- and out-neighbours) form the contiguous window
-// [lo, hi) computed by the plan; the window's slab of xl (and xr / g / y in backward) is staged in shared
-// memory by ONE bulk-TMA copy per array (cp.async.bulk, 16-byte aligned middle) plus a ragged <16-byte head
-// and tail.  Windows that do not fit the shared-memory budget (arbitrary, non-banded graphs) fall back to
-// gathering neighbour rows straight from global memory (L2) -- same code, template flag SM = false.
+// Lanes: a consumer warp owns 32 / Hp consecutive nodes (Hp = heads padded to a power of two); lane = (node, head)
+// with the head index in the HIGH lane bits, so that the 8-byte shared-memory loads of a half-warp hit 16 different
+// rows of one head: conflict-free at the row stride of 22 floats.  The per-destination softmax needs no cross-lane
+// traffic and nothing is atomic.
 //
-// Arithmetic: the kernels are instruction-issue bound (ncu: 79 % issue-active, DRAM traffic == algorithmic bytes), so
-// the per-channel math runs on Blackwell's packed fp32 pipe: a lane's C channels are held as ceil(C/2) float2 pairs
-// (zero padded) and every add / mul / fma is an FADD2 / FMUL2 / FFMA2.  LeakyReLU is max(s, slope*s), valid for the
-// slopes the C ABI accepts (0 <= slope <= 1; PyG's default 0.2).
+// Arithmetic: a lane's C channels are held as C/2 float2 pairs plus (odd C) one scalar.  Which channels pair up is
+// chosen per lane from the PARITY of its chunk's element offset, so every pair is an aligned 8-byte (fp32) / 4-byte
+// (bf16) shared-memory load; all math runs position-wise on the packed fp32 pipe (FADD2 / FFMA2).  LeakyReLU is
+// folded into the attention dot product:  att . lrelu(s) = att_p . s + att_m . |s|  with att_p = att (1+slope)/2,
+// att_m = att (1-slope)/2 (FFMA2 takes |.| as a free source modifier), and log2(e) is folded into att_p / att_m so the
+// scores live in the exp2 domain.
 #pragma once
 #include "common.cuh"
 
@@ -26,71 +29,201 @@ __host__ __device__ __forceinline__ uint32_t round16(uint32_t b) { return (b + 1
 // Channel counts the edge kernels are instantiated for (C = out_channels per head).
 #define TG_FOR_EACH_C(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(11) X(12) X(16) X(24) X(32)
 
-template <typename ST>
-struct Round {  // rounding applied by the reference's dtype flow to (xl_j + xr_i) and to leaky_relu(.)
-    static __device__ __forceinline__ float2 r(float2 v) { return v; }
+constexpr int kMaxStages = 4;
+constexpr int kEdgeSmemBudget = 226 * 1024;  // dynamic shared memory per CTA we are willing to request (1 CTA / SM)
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kOverflowGuard = 1e24f;  // softmax sums beyond this re-run the row with the exact maximum as shift
+
+// ---- channel vector ----------------------------------------------------------------------------------------------
+template <int C>
+struct CV {
+    static constexpr int NP = C / 2;
+    static constexpr bool ODD = (C & 1) != 0;
+    float2 p[NP > 0 ? NP : 1];
+    float s;
 };
-template <>
-struct Round<__nv_bfloat16> {  // under autocast both are bf16 tensors
-    static __device__ __forceinline__ float2 r(float2 v) { return __bfloat1622float2(__float22bfloat162_rn(v)); }
-};
+template <int C>
+__device__ __forceinline__ void cv_zero(CV<C> &v) {
+#pragma unroll
+    for (int i = 0; i < CV<C>::NP; ++i) v.p[i] = make_float2(0.f, 0.f);
+    v.s = 0.f;
+}
+// position of channel c in the lane's arrangement: par = 0 -> pairs (0,1)(2,3).. single C-1; par = 1 -> single 0, pairs (1,2)(3,4)..
+template <int C>
+__device__ __forceinline__ int cv_channel_of_pair(int i, int par) { return 2 * i + par; }
+template <int C>
+__device__ __forceinline__ int cv_channel_of_single(int par) { return par ? 0 : C - 1; }
 
-// C elements of storage type ST -> ceil(C/2) float2 pairs (odd C: the last .y is zero)
-template <int C>
-__device__ __forceinline__ void load_row(const float *__restrict__ p, float2 (&v)[(C + 1) / 2]) {
-#pragma unroll
-    for (int i = 0; i < C / 2; ++i) v[i] = make_float2(p[2 * i], p[2 * i + 1]);
-    if (C & 1) v[C / 2] = make_float2(p[C - 1], 0.f);
+__device__ __forceinline__ float2 bf16x2_to_float2(uint32_t u) {
+    return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xFFFF0000u));
 }
-template <int C>
-__device__ __forceinline__ void load_row(const __nv_bfloat16 *__restrict__ p, float2 (&v)[(C + 1) / 2]) {
-#pragma unroll
-    for (int i = 0; i < C / 2; ++i) v[i] = make_float2(__bfloat162float(p[2 * i]), __bfloat162float(p[2 * i + 1]));
-    if (C & 1) v[C / 2] = make_float2(__bfloat162float(p[C - 1]), 0.f);
+__device__ __forceinline__ uint32_t float2_to_bf16x2(float2 v) {
+    const __nv_bfloat162 b = __float22bfloat162_rn(v);
+    return *reinterpret_cast<const uint32_t *>(&b);
 }
-template <int C>
-__device__ __forceinline__ void store_row(float *p, const float2 (&v)[(C + 1) / 2]) {
+
+// Load the C channels starting at `chunk` (channel 0).  VEC: `chunk + par` is pair-aligned -> vector loads.
+template <int C, bool VEC>
+__device__ __forceinline__ void cv_load(CV<C> &v, const float *chunk, int par) {
+    const float *q = chunk + par;
 #pragma unroll
-    for (int i = 0; i < C / 2; ++i) {
-        p[2 * i] = v[i].x;
-        p[2 * i + 1] = v[i].y;
+    for (int i = 0; i < CV<C>::NP; ++i) {
+        if (VEC) v.p[i] = *reinterpret_cast<const float2 *>(q + 2 * i);
+        else v.p[i] = make_float2(q[2 * i], q[2 * i + 1]);
     }
-    if (C & 1) p[C - 1] = v[C / 2].x;
+    if (CV<C>::ODD) v.s = chunk[par ? 0 : C - 1];
+}
+template <int C, bool VEC>
+__device__ __forceinline__ void cv_load(CV<C> &v, const __nv_bfloat16 *chunk, int par) {
+    const __nv_bfloat16 *q = chunk + par;
+#pragma unroll
+    for (int i = 0; i < CV<C>::NP; ++i) {
+        if (VEC) v.p[i] = bf16x2_to_float2(*reinterpret_cast<const uint32_t *>(q + 2 * i));
+        else v.p[i] = make_float2(__bfloat162float(q[2 * i]), __bfloat162float(q[2 * i + 1]));
+    }
+    if (CV<C>::ODD) v.s = __bfloat162float(chunk[par ? 0 : C - 1]);
+}
+template <int C, bool VEC>
+__device__ __forceinline__ void cv_store(float *chunk, const CV<C> &v, int par) {
+    float *q = chunk + par;
+#pragma unroll
+    for (int i = 0; i < CV<C>::NP; ++i) {
+        if (VEC) *reinterpret_cast<float2 *>(q + 2 * i) = v.p[i];
+        else { q[2 * i] = v.p[i].x; q[2 * i + 1] = v.p[i].y; }
+    }
+    if (CV<C>::ODD) chunk[par ? 0 : C - 1] = v.s;
+}
+template <int C, bool VEC>
+__device__ __forceinline__ void cv_store(__nv_bfloat16 *chunk, const CV<C> &v, int par) {
+    __nv_bfloat16 *q = chunk + par;
+#pragma unroll
+    for (int i = 0; i < CV<C>::NP; ++i) {
+        if (VEC) *reinterpret_cast<uint32_t *>(q + 2 * i) = float2_to_bf16x2(v.p[i]);
+        else { q[2 * i] = __float2bfloat16_rn(v.p[i].x); q[2 * i + 1] = __float2bfloat16_rn(v.p[i].y); }
+    }
+    if (CV<C>::ODD) chunk[par ? 0 : C - 1] = __float2bfloat16_rn(v.s);
+}
+// parameters (att, bias): element-wise loads in the lane's arrangement, scaled
+template <int C>
+__device__ __forceinline__ void cv_load_param(CV<C> &v, const float *p, int par, float scale) {
+#pragma unroll
+    for (int i = 0; i < CV<C>::NP; ++i) v.p[i] = make_float2(p[2 * i + par] * scale, p[2 * i + 1 + par] * scale);
+    v.s = CV<C>::ODD ? p[par ? 0 : C - 1] * scale : 0.f;
 }
 template <int C>
-__device__ __forceinline__ void store_row(__nv_bfloat16 *p, const float2 (&v)[(C + 1) / 2]) {
+__device__ __forceinline__ float cv_dot(const CV<C> &a, const CV<C> &b) {
+    float2 d = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int i = 0; i < C / 2; ++i) {
-        p[2 * i] = __float2bfloat16_rn(v[i].x);
-        p[2 * i + 1] = __float2bfloat16_rn(v[i].y);
+    for (int i = 0; i < CV<C>::NP; ++i) d = __ffma2_rn(a.p[i], b.p[i], d);
+    float r = d.x + d.y;
+    if (CV<C>::ODD) r = fmaf(a.s, b.s, r);
+    return r;
+}
+__device__ __forceinline__ float2 abs2(float2 v) { return make_float2(fabsf(v.x), fabsf(v.y)); }
+__device__ __forceinline__ float2 splat(float v) { return make_float2(v, v); }
+
+// score of one edge in the exp2 domain, WITHOUT the destination constant att_p . xr_i:
+//     att_p . xj + att_m . |xj + xr|        (s = xj + xr is returned for the backward)
+template <int C>
+__device__ __forceinline__ float edge_score(const CV<C> &attp, const CV<C> &attm, const CV<C> &xj, const CV<C> &xr, CV<C> &s) {
+    float2 el = make_float2(0.f, 0.f), ea = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < CV<C>::NP; ++i) {
+        s.p[i] = __fadd2_rn(xj.p[i], xr.p[i]);
+        el = __ffma2_rn(attp.p[i], xj.p[i], el);
+        ea = __ffma2_rn(attm.p[i], abs2(s.p[i]), ea);
     }
-    if (C & 1) p[C - 1] = __float2bfloat16_rn(v[C / 2].x);
+    float e = (el.x + ea.x) + (el.y + ea.y);
+    if (CV<C>::ODD) {
+        s.s = xj.s + xr.s;
+        e += fmaf(attm.s, fabsf(s.s), attp.s * xj.s);
+    }
+    return e;
 }
 
-// s = xj + xr, z = LeakyReLU(s), returns e = att . z   (identical instruction sequence in forward and backward, so the
-// alpha recomputed in backward matches the saved softmax statistics)
-template <int C, typename ST>
-__device__ __forceinline__ float edge_score(const float2 (&att)[(C + 1) / 2], const float2 (&xj)[(C + 1) / 2],
-                                            const float2 (&xr)[(C + 1) / 2], float2 slope2, float2 (&s)[(C + 1) / 2],
-                                            float2 (&z)[(C + 1) / 2]) {
-    float2 e2 = make_float2(0.f, 0.f);
-#pragma unroll
-    for (int i = 0; i < (C + 1) / 2; ++i) {
-        s[i] = Round<ST>::r(__fadd2_rn(xj[i], xr[i]));
-        const float2 t = __fmul2_rn(s[i], slope2);
-        z[i] = Round<ST>::r(make_float2(fmaxf(s[i].x, t.x), fmaxf(s[i].y, t.y)));
-        e2 = __ffma2_rn(att[i], z[i], e2);
-    }
-    return e2.x + e2.y;
-}
-
-__device__ __forceinline__ float hsum(float2 v) { return v.x + v.y; }
-
-// 2^x for x <= 0 (softmax weights): bare MUFU.EX2, flush-to-zero -- no denormal rescue sequence
+// 2^x, bare MUFU.EX2 with flush-to-zero (softmax weights; no denormal rescue sequence)
 __device__ __forceinline__ float fast_exp2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+__device__ __forceinline__ float fast_log2(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// ---- lane <-> (node, head) ----------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ int pad_heads(int H) {  // next power of two (<= 32)
+    int hp = 1;
+    while (hp < H) hp <<= 1;
+    return hp;
+}
+
+// ---- item schedule ---------------------------------------------------------------------------------------------
+struct ItemRange {
+    int64_t w0, w1;
+};
+__device__ __forceinline__ ItemRange cta_items(int64_t items) {
+    ItemRange r;
+    r.w0 = items * blockIdx.x / gridDim.x;
+    r.w1 = items * (blockIdx.x + 1) / gridDim.x;
+    return r;
+}
+
+// ring position: stage index and mbarrier phase parity, advanced without divisions
+struct Ring {
+    int st;
+    uint32_t ph;
+    __device__ __forceinline__ void advance(int num_stages) {
+        if (++st == num_stages) {
+            st = 0;
+            ph ^= 1u;
+        }
+    }
+};
+
+// tile table: shared memory when it fits (kMetaSmemTiles), global memory (L1 / L2) otherwise
+constexpr int kMetaSmemTiles = 64;
+__device__ __forceinline__ tg_tile_meta load_meta(const tg_tile_meta *smem_tab, const tg_tile_meta *gmem_tab, int num_tiles, int tile) {
+    const tg_tile_meta *src = num_tiles <= kMetaSmemTiles ? smem_tab + tile : gmem_tab + tile;
+    const int4 a = reinterpret_cast<const int4 *>(src)[0], b = reinterpret_cast<const int4 *>(src)[1];
+    tg_tile_meta m;
+    m.lo = a.x; m.hi = a.y; m.kin_kout = a.z; m.eligible = a.w;
+    m.slab_off = (int64_t)(uint32_t)b.x | ((int64_t)b.y << 32);
+    m.slab_bytes = b.z; m.pad = b.w;
+    return m;
+}
+
+// Copy of the rows [r0, r0 + nrows) of a row-major array (row = RB bytes, 16-byte aligned base, Rtot rows) as ONE
+// bulk-TMA transfer: the range is widened to the array's 16-byte row period `per` (a power of two: 16 / gcd(16, RB)),
+// clamped to the array.  Row r0 then sits `skip` bytes into the shared region.  `tail` (< 16 bytes) is non-zero only
+// when the clamped end of the array is not 16-byte aligned (last rows of the last snapshot): plain copies.
+struct WinCopy {
+    const unsigned char *src;
+    uint32_t mid, tail, skip;
+};
+__device__ __forceinline__ WinCopy win_copy(const void *base, int64_t r0, int nrows, uint32_t RB, int per, int64_t Rtot) {
+    const int64_t ra = r0 & ~(int64_t)(per - 1);
+    int64_t rb = (r0 + nrows + per - 1) & ~(int64_t)(per - 1);
+    if (rb > Rtot) rb = Rtot;
+    const uint32_t bytes = (uint32_t)(rb - ra) * RB;
+    WinCopy c;
+    c.src = static_cast<const unsigned char *>(base) + ra * RB;
+    c.mid = bytes & ~15u;
+    c.tail = bytes - c.mid;
+    c.skip = (uint32_t)(r0 - ra) * RB;
+    return c;
+}
+__device__ __forceinline__ uint32_t win_skip(int64_t r0, uint32_t RB, int per) { return (uint32_t)(r0 & (int64_t)(per - 1)) * RB; }
+__device__ __forceinline__ void win_copy_tail(const WinCopy &c, unsigned char *dst, int lane) {  // rare (see WinCopy)
+    for (uint32_t b = 2u * lane; b < c.tail; b += 64u)
+        *reinterpret_cast<uint16_t *>(dst + c.mid + b) = *reinterpret_cast<const uint16_t *>(c.src + c.mid + b);
+}
+__host__ __device__ __forceinline__ int row_period(uint32_t RB) {  // rows after which the byte offset is 16-byte aligned again
+    int per = 1;
+    while ((uint64_t(per) * RB) % 16u) per <<= 1;
+    return per;
 }
 
 }  // namespace tg

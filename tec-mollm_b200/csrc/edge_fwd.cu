@@ -1,8 +1,18 @@
 // edge_fwd.cu -- fused GATv2 edge phase, forward: for every snapshot and destination node
 //     e_ij = att . LeakyReLU(xl_j + xr_i),  alpha = softmax_j(e_ij),  y_i = sum_j alpha_ij q_ij xl_j + bias
-// in ONE kernel (PyG: gather, add, leaky_relu, mul, sum, scatter-max, exp, scatter-add, div, dropout, mul,
+// in ONE persistent kernel (PyG: gather, add, leaky_relu, mul, sum, scatter-max, exp, scatter-add, div, dropout, mul,
 // scatter-add, bias = ~20 ATen launches and 4-6 materialised (S*E, H, C) tensors; SURVEY.md K4-K9, reached
-// from /root/reference/src/model/modules.py:356).  Online softmax per lane, no atomics, no cross-lane traffic.
+// from /root/reference/src/model/modules.py:356).  Execution model, lane mapping and arithmetic: edge_common.cuh.
+//
+// Softmax without a running maximum: softmax is shift invariant, so the row's SELF-LOOP score (CSR slot 0, always
+// present) is the shift -- one exp2 per edge, no rescaling of the accumulator.  A row whose sum leaves the safe fp32
+// range (scores more than ~80 log2-units above the self loop: never on sane data) is redone with the exact maximum.
+// Saved for backward: ONE float per (row, head), stat = shift + log2(sum), i.e. alpha_ij = exp2(e_ij - stat).
+#include <algorithm>
+#include <cstdlib>
+#include <utility>
+#include <vector>
+
 #include "edge_common.cuh"
 
 namespace tg {
@@ -10,134 +20,326 @@ namespace tg {
 struct EdgeFwdArgs {
     const void *xl, *xr;
     const float *att, *bias;
-    float *y, *m, *den;
-    const int32_t *rowptr, *col, *tile_lo, *tile_hi;
-    int32_t N, T, num_tiles, S, H;
-    int64_t E;
+    float *y, *stat;
+    const tg_tile_meta *meta;
+    const unsigned char *slabs;
+    const int32_t *rowptr, *col;  // destination-sorted CSR (tiles that are not staged)
+    int32_t N, T, num_tiles, S, H, npw;
     float slope, inv_keep;
     uint32_t drop_thr;
     uint64_t seed;
     int32_t literal;
-    int32_t win_rows_smem;  // rows of the xl window that fit in the shared-memory slab
+    int32_t cap_rows, cap_k, num_stages;
+    int32_t per;  // 16-byte row period of xl / xr (rows)
+    // shared-memory map (bytes): [barriers 128][tile table][y staging][stage 0][stage 1]..;  stage: [slab][xr tile][xl window]
+    uint32_t stage_bytes, off_meta, off_stage0, off_xr, off_xl, off_y;
+    int64_t items;
 };
 
-template <int C, typename ST, bool SM>
-__device__ __forceinline__ void edge_fwd_body(const EdgeFwdArgs &a, unsigned char *smem_raw) {
-    constexpr int CP = (C + 1) / 2;
-    const int tid = threadIdx.x;
-    const int tile = blockIdx.x % a.num_tiles;
-    const int snap = blockIdx.x / a.num_tiles;
-    const int H = a.H, HC = H * C;
-    const int n0 = tile * a.T;
-    const int n1 = min(a.N, n0 + a.T);
-    const int nt = n1 - n0;
-    const bool self_only = a.literal && snap > 0;  // modules.py:353-356 as written: rows >= N have no edges
-    int lo = a.tile_lo[tile], hi = a.tile_hi[tile];
-    if (self_only) { lo = n0; hi = n1; }
-    const int win = hi - lo;
+// one (destination node, head): everything between "inputs are readable" and "y / stat are known".
+// The self loop (CSR slot 0) is peeled: it uses the lane's own xl row and its score is the softmax shift.  The other
+// slots are walked TWO per iteration, branch-free (slots past the lane's degree read a valid row and get weight 0), so
+// the two edges' instruction streams interleave.
+template <int C, typename ST, bool VEC, bool FAST>
+__device__ __forceinline__ void fwd_lane(const EdgeFwdArgs &a, const CV<C> &attp, const CV<C> &attm, const CV<C> &bias_h,
+                                         const ST *xr_chunk, const ST *xl_self /* own row, + h*C */,
+                                         const ST *xl_lane /* window row 0 (FAST) or snapshot row 0, + h*C */, int HC, int par,
+                                         const uint16_t *ell /* + node_l */, const int32_t *col /* + k0 */, int deg, int kmax_w,
+                                         uint32_t slot0, uint32_t key, CV<C> &out, float &stat) {
+    CV<C> xr_i, xl_i, acc;
+    if (deg > 0) {
+        cv_load<C, VEC>(xr_i, xr_chunk, par);
+        cv_load<C, VEC>(xl_i, xl_self, par);
+    } else {
+        cv_zero(xr_i);
+        cv_zero(xl_i);
+    }
+    const float wself = deg > 0 ? 1.f : 0.f;
+    float shift, l = 0.f;
+    {
+        CV<C> s;
+        shift = edge_score<C>(attp, attm, xl_i, xr_i, s);
+    }
+    const float e_self = shift;
+    const int Ts = (a.T + 7) & ~7;
+    auto nbr = [&](int k) -> int {
+        if (FAST) return (int)ell[k * Ts];
+        return k < deg ? __ldg(col + k) : 0;
+    };
+    auto keep = [&](float w, int k) -> float {
+        if (!a.drop_thr) return w;
+        return dropout_bits(key, slot0 + (uint32_t)k) >= a.drop_thr ? w * a.inv_keep : 0.f;
+    };
+#pragma unroll 1
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        {
+            const float w = wself * fast_exp2(e_self - shift);
+            l = w;
+            const float wq = keep(w, 0);
+            const float2 wq2 = splat(wq);
+#pragma unroll
+            for (int i = 0; i < CV<C>::NP; ++i) acc.p[i] = __fmul2_rn(wq2, xl_i.p[i]);
+            acc.s = wq * xl_i.s;
+        }
+#pragma unroll 1
+        for (int k = 1; k < kmax_w; k += 2) {
+            const int ja = nbr(k), jb = nbr(k + 1);
+            CV<C> xa, xb, sa, sb;
+            cv_load<C, VEC>(xa, xl_lane + (FAST ? (ptrdiff_t)(ja * HC) : (ptrdiff_t)ja * HC), par);
+            cv_load<C, VEC>(xb, xl_lane + (FAST ? (ptrdiff_t)(jb * HC) : (ptrdiff_t)jb * HC), par);
+            const float ea = edge_score<C>(attp, attm, xa, xr_i, sa);
+            const float eb = edge_score<C>(attp, attm, xb, xr_i, sb);
+            // branch-free validity: slots past the degree read a real row (finite score), weight 0.  The clamp keeps
+            // 0 * exp2(.) finite there and still trips the overflow guard (2^100 > kOverflowGuard) for real edges.
+            const float va = k < deg ? 1.f : 0.f, vb = k + 1 < deg ? 1.f : 0.f;
+            const float wa = va * fast_exp2(fminf(ea - shift, 100.f));
+            const float wb = vb * fast_exp2(fminf(eb - shift, 100.f));
+            l += wa + wb;
+            const float2 qa = splat(keep(wa, k)), qb = splat(keep(wb, k + 1));
+#pragma unroll
+            for (int i = 0; i < CV<C>::NP; ++i) acc.p[i] = __ffma2_rn(qb, xb.p[i], __ffma2_rn(qa, xa.p[i], acc.p[i]));
+            if (CV<C>::ODD) acc.s = fmaf(qb.x, xb.s, fmaf(qa.x, xa.s, acc.s));
+        }
+        const bool ok = l < kOverflowGuard;  // false for inf / nan as well
+        if (__all_sync(0xFFFFFFFFu, ok) || attempt == 1) break;
+        float mx = e_self;  // rare: exact maximum, then redo the row
+        for (int k = 1; k < deg; ++k) {
+            CV<C> xj, s;
+            const int j = nbr(k);
+            cv_load<C, VEC>(xj, xl_lane + (FAST ? (ptrdiff_t)(j * HC) : (ptrdiff_t)j * HC), par);
+            mx = fmaxf(mx, edge_score<C>(attp, attm, xj, xr_i, s));
+        }
+        shift = mx;
+    }
+    const float inv = l > 0.f ? __frcp_rn(l) : 0.f;
+    const float2 inv2 = splat(inv);
+#pragma unroll
+    for (int i = 0; i < CV<C>::NP; ++i) out.p[i] = __ffma2_rn(acc.p[i], inv2, bias_h.p[i]);
+    out.s = fmaf(acc.s, inv, bias_h.s);
+    stat = l > 0.f ? shift + fast_log2(l) : 0.f;
+}
 
-    const ST *xl_g = static_cast<const ST *>(a.xl) + (static_cast<int64_t>(snap) * a.N + lo) * HC;
-    const ST *xr_g = static_cast<const ST *>(a.xr) + (static_cast<int64_t>(snap) * a.N + n0) * HC;
-
-    // shared layout: [mbarrier 16][xr slab + 16][y tile fp32][xl window + 16]
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
-    unsigned char *xr_base = smem_raw + 16;
-    float *y_s = reinterpret_cast<float *>(xr_base + round16(a.T * HC * sizeof(ST)) + 16);
-    unsigned char *xl_base = reinterpret_cast<unsigned char *>(y_s) + round16(a.T * HC * sizeof(float));
-
-    const CopyPlan cr = plan_copy(xr_g, xr_base, nt * HC * (uint32_t)sizeof(ST));
-    const CopyPlan cl = plan_copy(xl_g, xl_base, SM ? win * HC * (uint32_t)sizeof(ST) : 0u);
-    if (tid == 0) {
-        mbar_init(bar, 1);
+template <int C, typename ST, bool VEC>
+__global__ void __launch_bounds__(512, 1) edge_fwd_kernel(const EdgeFwdArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem);
+    uint64_t *empty = full + kMaxStages;
+    const tg_tile_meta *meta_s = reinterpret_cast<const tg_tile_meta *>(smem + a.off_meta);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ncw = (blockDim.x >> 5) - 1;  // consumer warps; the last warp is the producer
+    const int H = a.H, HC = H * C, T = a.T, N = a.N;
+    const int Ts = (T + 7) & ~7;  // row stride of the slab sections
+    const int NS = a.num_stages;
+    constexpr uint32_t ES = sizeof(ST);
+    const uint32_t RB = (uint32_t)HC * ES;  // bytes of one xl / xr row
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], ncw);
+        }
         fence_mbar_init();
     }
+    if (a.num_tiles <= kMetaSmemTiles)
+        for (int i = threadIdx.x; i < a.num_tiles * 8; i += blockDim.x)
+            reinterpret_cast<int32_t *>(smem + a.off_meta)[i] = reinterpret_cast<const int32_t *>(a.meta)[i];
     __syncthreads();
-    if (tid == 0) {
-        mbar_arrive_expect_tx(bar, cr.mid + cl.mid);
-        issue_copy_bulk(cr, bar);
-        issue_copy_bulk(cl, bar);
-    }
-    copy_ragged(cr, tid);
-    copy_ragged(cl, tid);
-    __syncthreads();
-    mbar_wait(bar, 0);
+    const ItemRange R = cta_items(a.items);
+    int snap = (int)(R.w0 / a.num_tiles), tile = (int)(R.w0 % a.num_tiles);
+    const int64_t Rtot = (int64_t)a.S * N;
+    Ring ring{0, 0u};
 
-    const int node_l = tid / H;
-    const int h = tid - node_l * H;
-    if (node_l < nt) {
-        const int d = n0 + node_l;
-        float2 xr_i[CP], att_h[CP], acc[CP];
-        load_row<C>(reinterpret_cast<const ST *>(cr.s) + node_l * HC + h * C, xr_i);
-        load_row<C>(a.att + h * C, att_h);
-#pragma unroll
-        for (int i = 0; i < CP; ++i) acc[i] = make_float2(0.f, 0.f);
-        const int k1 = __ldg(a.rowptr + d + 1);
-        const int k0 = self_only ? k1 - 1 : __ldg(a.rowptr + d);  // the self loop is the row's last slot
-        // neighbour rows: shared window (SM) or global/L2 gather (window too large for shared memory)
-        const ST *src_base = (SM ? reinterpret_cast<const ST *>(cl.s) : xl_g) + h * C;
-        const uint32_t key = a.drop_thr ? dropout_snapshot_key(a.seed, (uint32_t)snap) : 0u;
-        const float2 slope2 = make_float2(a.slope, a.slope);
-        constexpr float kLog2e = 1.4426950408889634f;
-        float mx = -INFINITY, l = 0.f;  // running max (log2 domain) and running sum
-        for (int k = k0; k < k1; ++k) {
-            const int j = __ldg(a.col + k) - lo;
-            float2 xj[CP], s[CP], z[CP];
-            load_row<C>(src_base + j * HC, xj);
-            const float e = edge_score<C, ST>(att_h, xj, xr_i, slope2, s, z) * kLog2e;
-            float q = 1.f;
-            if (a.drop_thr) q = dropout_bits16(key, (uint32_t)k, (uint32_t)h) >= a.drop_thr ? a.inv_keep : 0.f;
-            const float mn = fmaxf(mx, e);
-            const float sc = fast_exp2(mx - mn);
-            const float pe = fast_exp2(e - mn);
-            l = fmaf(l, sc, pe);
-            const float2 sc2 = make_float2(sc, sc), w2 = make_float2(pe * q, pe * q);
-#pragma unroll
-            for (int i = 0; i < CP; ++i) acc[i] = __ffma2_rn(acc[i], sc2, __fmul2_rn(w2, xj[i]));
-            mx = mn;
+    if (warp == ncw) {
+        // ================================ producer warp ================================
+        for (int64_t w = R.w0; w < R.w1; ++w) {
+            const tg_tile_meta m = load_meta(meta_s, a.meta, a.num_tiles, tile);
+            const int n0 = tile * T, nt = min(N, n0 + T) - n0;
+            const bool lit = a.literal && snap > 0;
+            const int lo = lit ? n0 : m.lo, win = lit ? nt : m.hi - m.lo;
+            const bool staged = m.eligible && win <= a.cap_rows && (m.kin_kout & 0xFFFF) <= a.cap_k;
+            if (staged) {
+                unsigned char *stage = smem + a.off_stage0 + (size_t)ring.st * a.stage_bytes;
+                const WinCopy cr = win_copy(a.xr, (int64_t)snap * N + n0, nt, RB, a.per, Rtot);
+                const WinCopy cl = win_copy(a.xl, (int64_t)snap * N + lo, win, RB, a.per, Rtot);
+                if (lane == 0) mbar_wait(&empty[ring.st], ring.ph ^ 1u);
+                __syncwarp();
+                if (cr.tail | cl.tail) {  // only the last rows of the last snapshot
+                    win_copy_tail(cr, stage + a.off_xr, lane);
+                    win_copy_tail(cl, stage + a.off_xl, lane);
+                    __syncwarp();
+                }
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(&full[ring.st], (uint32_t)m.slab_bytes + cr.mid + cl.mid);
+                    bulk_g2s(stage, a.slabs + m.slab_off, (uint32_t)m.slab_bytes, &full[ring.st]);
+                    if (cr.mid) bulk_g2s(stage + a.off_xr, cr.src, cr.mid, &full[ring.st]);
+                    if (cl.mid) bulk_g2s(stage + a.off_xl, cl.src, cl.mid, &full[ring.st]);
+                }
+                ring.advance(NS);
+            }
+            if (++tile == a.num_tiles) { tile = 0; ++snap; }
         }
-        const float den = l + 1e-16f;
-        const float inv = 1.f / den;
-        float2 bias_h[CP], out[CP];
-        load_row<C>(a.bias + h * C, bias_h);
-        const float2 inv2 = make_float2(inv, inv);
-#pragma unroll
-        for (int i = 0; i < CP; ++i) out[i] = __ffma2_rn(acc[i], inv2, bias_h[i]);
-        store_row<C>(y_s + node_l * HC + h * C, out);
-        const int64_t r = (static_cast<int64_t>(snap) * a.N + d) * H + h;
-        a.m[r] = mx;   // softmax shift in the log2 domain (m * log2 e); consumed only by edge_bwd
-        a.den[r] = den;
+        return;
     }
-    __syncthreads();
-    float *y_g = a.y + (static_cast<int64_t>(snap) * a.N + n0) * HC;
-    for (int i = tid; i < nt * HC; i += blockDim.x) y_g[i] = y_s[i];
+
+    // ================================ consumer warps ================================
+    const int npw = a.npw;                 // nodes per warp = 32 / padded heads
+    const int nw = lane & (npw - 1);       // node within the warp (npw is a power of two)
+    const int h = lane / npw;              // head (>= H: padding lane)
+    const int node_l = warp * npw + nw;
+    const bool head_ok = h < H;
+    const int hh = head_ok ? h : 0;
+    const int par = VEC ? ((hh * C) & 1) : 0;
+    CV<C> attp, attm, bias_h;
+    cv_load_param<C>(attp, a.att + hh * C, par, 0.5f * (1.f + a.slope) * kLog2e);
+    cv_load_param<C>(attm, a.att + hh * C, par, 0.5f * (1.f - a.slope) * kLog2e);
+    cv_load_param<C>(bias_h, a.bias + hh * C, par, 1.f);
+    float *ybuf = reinterpret_cast<float *>(smem + a.off_y) + warp * npw * HC;
+    const uint32_t head_key = dropout_head_key((uint32_t)hh);
+    uint32_t key = 0;
+    int key_snap = -1;
+
+    for (int64_t w = R.w0; w < R.w1; ++w) {
+        const tg_tile_meta m = load_meta(meta_s, a.meta, a.num_tiles, tile);
+        const int n0 = tile * T, nt = min(N, n0 + T) - n0;
+        const bool lit = a.literal && snap > 0;
+        const int lo = lit ? n0 : m.lo, win = lit ? nt : m.hi - m.lo;
+        const bool staged = m.eligible && win <= a.cap_rows && (m.kin_kout & 0xFFFF) <= a.cap_k;
+        const bool active = head_ok && node_l < nt;
+        const int64_t row = (int64_t)snap * N + n0 + node_l;
+        if (a.drop_thr && snap != key_snap) {
+            key = dropout_snapshot_key(a.seed, (uint32_t)snap) ^ head_key;
+            key_snap = snap;
+        }
+        CV<C> out;
+        float stat = 0.f;
+        if (staged) {
+            const unsigned char *stage = smem + a.off_stage0 + (size_t)ring.st * a.stage_bytes;
+            const int32_t *k0s = reinterpret_cast<const int32_t *>(stage + 16);
+            const int32_t *degs = k0s + Ts;
+            const uint16_t *ell = reinterpret_cast<const uint16_t *>(degs + Ts) + node_l;
+            const ST *xr_s = reinterpret_cast<const ST *>(stage + a.off_xr + win_skip((int64_t)snap * N + n0, RB, a.per));
+            const ST *xl_s = reinterpret_cast<const ST *>(stage + a.off_xl + win_skip((int64_t)snap * N + lo, RB, a.per));
+            mbar_wait(&full[ring.st], ring.ph);
+            int deg = active ? (degs[node_l] & 0xFFFF) : 0;
+            if (lit) deg = min(deg, 1);
+            const uint32_t slot0 = active ? (uint32_t)k0s[node_l] : 0u;
+            const int kmax_w = __reduce_max_sync(0xFFFFFFFFu, deg);
+            fwd_lane<C, ST, VEC, true>(a, attp, attm, bias_h, xr_s + node_l * HC + hh * C, xl_s + (n0 + node_l - lo) * HC + hh * C,
+                                       xl_s + hh * C, HC, par, ell, nullptr, deg, kmax_w, slot0, key, out, stat);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[ring.st]);  // this warp no longer reads the stage
+            ring.advance(NS);
+            // stage y through the warp's private buffer, then write the warp's rows as one contiguous run
+            if (active) cv_store<C, VEC>(ybuf + nw * HC + hh * C, out, par);
+            __syncwarp();
+            const int nv = max(0, min(npw, nt - warp * npw));  // valid nodes of this warp
+            float *y_g = a.y + ((int64_t)snap * N + n0 + warp * npw) * HC;
+            if (VEC) {
+                const float2 *src = reinterpret_cast<const float2 *>(ybuf);
+                float2 *dst = reinterpret_cast<float2 *>(y_g);
+                for (int i = lane; i < nv * HC / 2; i += 32) dst[i] = src[i];
+            } else {
+                for (int i = lane; i < nv * HC; i += 32) y_g[i] = ybuf[i];
+            }
+            __syncwarp();
+        } else {
+            // window or degree too large for a stage: gather straight from global memory (L2)
+            int deg = 0, k0 = 0;
+            if (active) {
+                k0 = __ldg(a.rowptr + n0 + node_l);
+                deg = __ldg(a.rowptr + n0 + node_l + 1) - k0;
+                if (lit) deg = min(deg, 1);
+            }
+            const int kmax_w = __reduce_max_sync(0xFFFFFFFFu, deg);
+            const ST *xl_snap = static_cast<const ST *>(a.xl) + (int64_t)snap * N * HC + hh * C;
+            const ST *xr_chunk = static_cast<const ST *>(a.xr) + row * HC + hh * C;
+            fwd_lane<C, ST, VEC, false>(a, attp, attm, bias_h, xr_chunk, xl_snap + (int64_t)(n0 + node_l) * HC, xl_snap, HC, par, nullptr,
+                                        a.col + k0, deg, kmax_w, (uint32_t)k0, key, out, stat);
+            if (active) cv_store<C, VEC>(a.y + row * HC + hh * C, out, par);
+        }
+        if (active) a.stat[row * H + hh] = stat;
+        if (++tile == a.num_tiles) { tile = 0; ++snap; }
+    }
 }
 
-template <int C, typename ST>
-__global__ void __launch_bounds__(256) edge_fwd_kernel(const EdgeFwdArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int tile = blockIdx.x % a.num_tiles;
-    const int snap = blockIdx.x / a.num_tiles;
-    int win = a.tile_hi[tile] - a.tile_lo[tile];
-    if (a.literal && snap > 0) win = min(a.N, (tile + 1) * a.T) - tile * a.T;
-    if (win <= a.win_rows_smem)
-        edge_fwd_body<C, ST, true>(a, smem_raw);
-    else
-        edge_fwd_body<C, ST, false>(a, smem_raw);
+// Choose how many ring stages and which tiles are staged: a tile is staged when its window and degree fit the stage.
+// Prefers 2+ stages (prefetch overlaps compute); falls back to 1 stage when that stages far more tiles.
+struct StagePick {
+    int num_stages, cap_rows, cap_k;
+    uint32_t stage_bytes, off_xr, off_xl;
+};
+static StagePick pick_stages(const tg_tiling &tl, int T, int HC, size_t es, int per, size_t fixed_bytes, int want_stages) {
+    const int Ts = (T + 7) & ~7;
+    StagePick best{0, 0, 0, 0, 0, 0};
+    double best_score = -1.0;
+    for (int ns = want_stages; ns >= 1; --ns) {
+        const size_t budget = (size_t(kEdgeSmemBudget) - fixed_bytes) / ns;
+        // candidate caps: every distinct (window, kin) of the tiles, largest first; take the largest that fits
+        int cap_rows = 0, cap_k = 0, staged = 0;
+        std::vector<std::pair<size_t, int>> need;  // (bytes, tile)
+        auto stage_bytes = [&](int rows, int k) {
+            const int slack = 2 * (per - 1);  // the copies are widened to the 16-byte row period
+            return size_t(round16(16 + 8 * Ts + 2 * Ts * k)) + round16(uint32_t((T + slack) * HC * es)) + round16(uint32_t((rows + slack) * HC * es));
+        };
+        for (int t = 0; t < tl.num_tiles; ++t)
+            if (tl.h_meta[t].eligible) need.push_back({stage_bytes(tl.h_meta[t].hi - tl.h_meta[t].lo, tl.h_meta[t].kin_kout & 0xFFFF), t});
+        std::sort(need.begin(), need.end());
+        for (auto &nt : need) {  // grow the caps tile by tile (cheapest first) while the joint stage still fits
+            const tg_tile_meta &m = tl.h_meta[nt.second];
+            const int r = std::max(cap_rows, std::max(m.hi - m.lo, T)), k = std::max(cap_k, m.kin_kout & 0xFFFF);
+            if (stage_bytes(r, k) > budget) break;
+            cap_rows = r;
+            cap_k = k;
+            ++staged;
+        }
+        if (!staged) continue;
+        const double frac = double(staged) / tl.num_tiles;
+        const double score = frac * (ns >= 2 ? 1.0 : 0.6);  // a single stage cannot overlap load and compute
+        if (score > best_score) {
+            best_score = score;
+            best.num_stages = ns;
+            best.cap_rows = cap_rows;
+            best.cap_k = cap_k;
+            best.off_xr = round16(16 + 8 * Ts + 2 * Ts * cap_k);
+            best.off_xl = best.off_xr + round16(uint32_t((T + 2 * (per - 1)) * HC * es));
+            best.stage_bytes = (uint32_t)stage_bytes(cap_rows, cap_k);
+        }
+        if (frac >= 0.9) break;
+    }
+    return best;
 }
 
-template <int C, typename ST>
-static int launch_fwd(const EdgeFwdArgs &a, int threads, size_t fixed_smem, int max_win, cudaStream_t st) {
-    EdgeFwdArgs b = a;
-    const int HC = a.H * C;
-    const size_t row_bytes = size_t(HC) * sizeof(ST);
-    int rows_fit = int((size_t(kSmemBudget) - fixed_smem - 16) / row_bytes);
-    b.win_rows_smem = rows_fit < max_win ? rows_fit : max_win;
-    if (b.win_rows_smem < 0) b.win_rows_smem = 0;
-    const size_t smem = fixed_smem + round16(uint32_t(b.win_rows_smem * row_bytes)) + 16;
-    auto kern = edge_fwd_kernel<C, ST>;
+template <int C, typename ST, bool VEC>
+static int launch_fwd(EdgeFwdArgs a, const tecgat_plan_t *plan, cudaStream_t st) {
+    const tg_tiling &tl = plan->fwd;
+    const int HC = a.H * C, T = tl.T;
+    const int hp = pad_heads(a.H);
+    a.npw = 32 / hp;
+    const int ncw = T / a.npw;  // consumer warps
+    const size_t ybytes = size_t(T) * HC * sizeof(float);
+    a.per = row_period(uint32_t(HC * sizeof(ST)));
+    a.off_meta = 128;
+    a.off_y = 128 + (tl.num_tiles <= kMetaSmemTiles ? tl.num_tiles * 32 : 0);
+    a.off_stage0 = (uint32_t)((a.off_y + ybytes + 127) & ~size_t(127));
+    const char *env = getenv("TECGAT_FWD_STAGES");  // tuning knob: ring depth wanted
+    const int want = env ? std::max(1, std::min(kMaxStages, atoi(env))) : 3;
+    const StagePick sp = pick_stages(tl, T, HC, sizeof(ST), a.per, a.off_stage0, want);
+    a.num_stages = sp.num_stages > 0 ? sp.num_stages : 1;
+    a.cap_rows = sp.cap_rows;
+    a.cap_k = sp.num_stages > 0 ? sp.cap_k : -1;  // -1: nothing is staged
+    a.stage_bytes = sp.stage_bytes;
+    a.off_xr = sp.off_xr;
+    a.off_xl = sp.off_xl;
+    const size_t smem = a.off_stage0 + size_t(a.num_stages) * a.stage_bytes;
+    auto kern = edge_fwd_kernel<C, ST, VEC>;
     TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t grid = int64_t(a.num_tiles) * a.S;
-    kern<<<(unsigned)grid, threads, smem, st>>>(b);
+    int dev = 0, sms = 0;
+    TG_CUDA(cudaGetDevice(&dev));
+    TG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int occ = 1;
+    TG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, (ncw + 1) * 32, smem));
+    if (occ < 1) occ = 1;
+    const int64_t grid = std::min<int64_t>(a.items, int64_t(sms) * occ);
+    kern<<<(unsigned)grid, (ncw + 1) * 32, smem, st>>>(a);
     TG_LAUNCH_CHECK();
     return TECGAT_OK;
 }
@@ -145,41 +347,43 @@ static int launch_fwd(const EdgeFwdArgs &a, int threads, size_t fixed_smem, int 
 }  // namespace tg
 
 extern "C" int tecgat_edge_fwd(const tecgat_plan_t *plan, const void *xl, const void *xr, const float *att,
-                               const float *bias, float *y, float *m, float *den, int32_t snapshots, int32_t heads,
+                               const float *bias, float *y, float *stat, int32_t snapshots, int32_t heads,
                                int32_t out_channels, float negative_slope, float dropout_p, uint64_t seed, int32_t mode,
                                int32_t dtype, void *stream) {
     using namespace tg;
-    TG_REQUIRE(plan && xl && xr && att && bias && y && m && den, TECGAT_EINVAL, "edge_fwd: NULL argument");
+    TG_REQUIRE(plan && xl && xr && att && bias && y && stat, TECGAT_EINVAL, "edge_fwd: NULL argument");
     TG_REQUIRE(snapshots > 0 && heads > 0 && out_channels > 0, TECGAT_EINVAL, "edge_fwd: non-positive size");
+    TG_REQUIRE(heads <= 32, TECGAT_ENOSUP, "edge_fwd: heads %d > 32", heads);
     TG_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, TECGAT_EINVAL, "edge_fwd: dropout_p %f outside [0, 1)", dropout_p);
-    TG_REQUIRE(negative_slope >= 0.f && negative_slope <= 1.f, TECGAT_ENOSUP, "edge_fwd: negative_slope %f outside [0, 1]", negative_slope);
     TG_REQUIRE(mode == TECGAT_MODE_SHARED || mode == TECGAT_MODE_LITERAL, TECGAT_EINVAL, "edge_fwd: bad mode %d", mode);
     TG_REQUIRE(dtype == TECGAT_F32 || dtype == TECGAT_BF16, TECGAT_EINVAL, "edge_fwd: bad dtype %d", dtype);
-    const int threads = ((plan->tile_nodes * heads + 31) / 32) * 32;
-    TG_REQUIRE(threads <= 256, TECGAT_ENOSUP, "edge_fwd: tile_nodes (%d) * heads (%d) exceeds 256 lanes; build the plan with a smaller tile",
-               plan->tile_nodes, heads);
-    TG_REQUIRE(int64_t(plan->num_tiles) * snapshots < (int64_t(1) << 31), TECGAT_ENOSUP, "edge_fwd: grid too large");
+    const int hp = pad_heads(heads);
+    const tg_tiling &tl = plan->fwd;
+    TG_REQUIRE(tl.T % (32 / hp) == 0 && tl.T * hp <= 480, TECGAT_ENOSUP,
+               "edge_fwd: forward tile of %d nodes x %d heads does not map onto <= 15 consumer warps; build the plan with "
+               "tile_nodes_fwd = a multiple of %d and <= %d", tl.T, heads, 32 / hp, 480 / hp);
+    const int HC = heads * out_channels;
+    const bool vec = (HC % 2) == 0;
+    TG_REQUIRE(reinterpret_cast<uintptr_t>(xl) % 16 == 0 && reinterpret_cast<uintptr_t>(xr) % 16 == 0 &&
+                   reinterpret_cast<uintptr_t>(y) % 16 == 0,
+               TECGAT_EINVAL, "edge_fwd: xl / xr / y must be 16-byte aligned");
     EdgeFwdArgs a;
-    a.xl = xl; a.xr = xr; a.att = att; a.bias = bias; a.y = y; a.m = m; a.den = den;
-    a.rowptr = plan->rowptr_in; a.col = plan->col_in; a.tile_lo = plan->tile_lo; a.tile_hi = plan->tile_hi;
-    a.N = plan->num_nodes; a.T = plan->tile_nodes; a.num_tiles = plan->num_tiles; a.S = snapshots; a.H = heads;
-    a.E = plan->num_edges;
+    a.xl = xl; a.xr = xr; a.att = att; a.bias = bias; a.y = y; a.stat = stat;
+    a.meta = tl.meta; a.slabs = tl.slabs;
+    a.rowptr = plan->rowptr_in; a.col = plan->col_in;
+    a.N = plan->num_nodes; a.T = tl.T; a.num_tiles = tl.num_tiles; a.S = snapshots; a.H = heads; a.npw = 0;
     a.slope = negative_slope;
-    a.drop_thr = dropout_p > 0.f ? dropout_threshold(dropout_p) : 0u;
+    a.drop_thr = dropout_p > 0.f ? std::max(1u, dropout_threshold(dropout_p)) : 0u;
     a.inv_keep = 1.f / (1.f - dropout_p);
     a.seed = seed;
     a.literal = (mode == TECGAT_MODE_LITERAL);
-    a.win_rows_smem = 0;
-    const int HC = heads * out_channels;
-    const size_t esz = dtype == TECGAT_F32 ? 4 : 2;
-    const size_t fixed = 16 + round16(uint32_t(a.T * HC * esz)) + 16 + round16(uint32_t(a.T * HC * 4));
-    TG_REQUIRE(fixed + 64 < size_t(kSmemBudget), TECGAT_ENOSUP, "edge_fwd: tile of %d nodes x %d channels does not fit shared memory",
-               a.T, HC);
+    a.items = int64_t(tl.num_tiles) * snapshots;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define TG_CASE(CC)                                                                                   \
-    case CC:                                                                                          \
-        return dtype == TECGAT_F32 ? launch_fwd<CC, float>(a, threads, fixed, plan->max_window, st)   \
-                                   : launch_fwd<CC, __nv_bfloat16>(a, threads, fixed, plan->max_window, st);
+#define TG_CASE(CC)                                                                                                   \
+    case CC:                                                                                                          \
+        if (vec) return dtype == TECGAT_F32 ? launch_fwd<CC, float, true>(a, plan, st) : launch_fwd<CC, __nv_bfloat16, true>(a, plan, st); \
+        if constexpr ((CC % 2) == 1) return dtype == TECGAT_F32 ? launch_fwd<CC, float, false>(a, plan, st) : launch_fwd<CC, __nv_bfloat16, false>(a, plan, st); \
+        break;
     switch (out_channels) {
         TG_FOR_EACH_C(TG_CASE)
         default:

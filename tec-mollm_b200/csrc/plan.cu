@@ -37,6 +37,13 @@ static int upload(T **dst, const std::vector<T> &src, cudaStream_t st) {
     return TECGAT_OK;
 }
 
+static void free_tiling(tg_tiling &t) {
+    cudaFree(t.meta);
+    cudaFree(t.slabs);
+    t.meta = nullptr;
+    t.slabs = nullptr;
+}
+
 extern "C" int tecgat_plan_destroy(tecgat_plan_t *p) {
     if (!p) return TECGAT_OK;
     cudaFree(p->rowptr_in);
@@ -44,8 +51,8 @@ extern "C" int tecgat_plan_destroy(tecgat_plan_t *p) {
     cudaFree(p->rowptr_out);
     cudaFree(p->col_out);
     cudaFree(p->slot_out);
-    cudaFree(p->tile_lo);
-    cudaFree(p->tile_hi);
+    free_tiling(p->fwd);
+    free_tiling(p->bwd);
     free(p->h_rowptr_in);
     free(p->h_col_in);
     free(p->h_eid_in);
@@ -53,15 +60,93 @@ extern "C" int tecgat_plan_destroy(tecgat_plan_t *p) {
     return TECGAT_OK;
 }
 
+// Build one tiling (see tg_tiling in common.cuh).  Forward tilings window the in-neighbours only; backward tilings
+// window in- and out-neighbours and carry the out-edge ELL + dropout slots as well.
+static int build_tiling(tg_tiling &tl, bool bwd, int32_t T, int64_t N, const std::vector<int32_t> &rp_in,
+                        const std::vector<int32_t> &col_in, const std::vector<int32_t> &rp_out,
+                        const std::vector<int32_t> &col_out, const std::vector<int32_t> &slot_out, cudaStream_t st) {
+    tl.T = T;
+    tl.bwd = bwd;
+    const int32_t Ts = (T + 7) & ~7;  // row stride of the slab sections: keeps every section 16-byte aligned
+    tl.num_tiles = static_cast<int32_t>((N + T - 1) / T);
+    tl.h_meta.resize(tl.num_tiles);
+    tl.h_slab_off.assign(tl.num_tiles + 1, 0);
+    for (int32_t t = 0; t < tl.num_tiles; ++t) {
+        const int64_t n0 = int64_t(t) * T, n1 = std::min<int64_t>(N, n0 + T);
+        int32_t l = static_cast<int32_t>(n0), h = static_cast<int32_t>(n1 - 1), kin = 0, kout = 0;
+        for (int64_t n = n0; n < n1; ++n) {
+            kin = std::max(kin, rp_in[n + 1] - rp_in[n]);
+            kout = std::max(kout, rp_out[n + 1] - rp_out[n]);
+        }
+        for (int32_t k = rp_in[n0]; k < rp_in[n1]; ++k) {
+            l = std::min(l, col_in[k]);
+            h = std::max(h, col_in[k]);
+        }
+        if (bwd)
+            for (int32_t k = rp_out[n0]; k < rp_out[n1]; ++k) {
+                l = std::min(l, col_out[k]);
+                h = std::max(h, col_out[k]);
+            }
+        // the kernels peel the self loop (slot 0) and walk the remaining slots two at a time: odd padded row counts
+        kin |= 1;
+        kout |= 1;
+        if (!bwd) kout = 0;
+        tg_tile_meta &m = tl.h_meta[t];
+        m.lo = l;
+        m.hi = h + 1;
+        bool ok = (h + 1 - l) <= 65535 && kin <= 65535 && kout <= 65535;
+        if (ok && bwd) ok = int64_t(rp_in[h + 1]) - rp_in[l] <= 65535;  // relative dropout slots fit uint16
+        m.eligible = ok ? 1 : 0;
+        m.kin_kout = ok ? (kin | (kout << 16)) : 0;
+        tl.max_window = std::max(tl.max_window, h + 1 - l);
+        const int64_t bytes = ok ? 16 + 8 * int64_t(Ts) + 2 * int64_t(Ts) * (kin + 2 * kout) : 0;
+        tl.h_slab_off[t + 1] = tl.h_slab_off[t] + ((bytes + 15) & ~int64_t(15));
+        m.slab_off = tl.h_slab_off[t];
+        m.slab_bytes = static_cast<int32_t>(tl.h_slab_off[t + 1] - tl.h_slab_off[t]);
+        m.pad = 0;
+    }
+    std::vector<unsigned char> slabs(static_cast<size_t>(std::max<int64_t>(tl.h_slab_off[tl.num_tiles], 16)), 0);
+    for (int32_t t = 0; t < tl.num_tiles; ++t) {
+        const tg_tile_meta &m = tl.h_meta[t];
+        if (!m.eligible) continue;
+        const int32_t kin = m.kin_kout & 0xFFFF, kout = m.kin_kout >> 16;
+        const int64_t n0 = int64_t(t) * T, n1 = std::min<int64_t>(N, n0 + T);
+        unsigned char *base = slabs.data() + tl.h_slab_off[t];
+        int32_t *hdr = reinterpret_cast<int32_t *>(base);
+        int32_t *k0 = hdr + 4, *deg = k0 + Ts;
+        uint16_t *ell_in = reinterpret_cast<uint16_t *>(deg + Ts);
+        uint16_t *ell_out = ell_in + size_t(kin) * Ts, *slot = ell_out + size_t(kout) * Ts;
+        hdr[0] = m.lo;
+        hdr[1] = m.hi;
+        hdr[2] = m.kin_kout;
+        hdr[3] = rp_in[m.lo];
+        for (int64_t n = n0; n < n1; ++n) {
+            const int32_t i = static_cast<int32_t>(n - n0), di = rp_in[n + 1] - rp_in[n], dout = bwd ? rp_out[n + 1] - rp_out[n] : 0;
+            k0[i] = rp_in[n];
+            deg[i] = di | (dout << 16);
+            for (int32_t k = 0; k < di; ++k) ell_in[size_t(k) * Ts + i] = static_cast<uint16_t>(col_in[rp_in[n] + k] - m.lo);
+            for (int32_t k = 0; k < dout; ++k) {
+                ell_out[size_t(k) * Ts + i] = static_cast<uint16_t>(col_out[rp_out[n] + k] - m.lo);
+                slot[size_t(k) * Ts + i] = static_cast<uint16_t>(slot_out[rp_out[n] + k] - rp_in[m.lo]);
+            }
+        }
+    }
+    int rc;
+    if ((rc = upload(&tl.meta, tl.h_meta, st)) || (rc = upload(&tl.slabs, slabs, st)))
+        return rc;
+    TG_CUDA(cudaStreamSynchronize(st));  // `slabs` is a local
+    return TECGAT_OK;
+}
+
 extern "C" int tecgat_plan_create(const int64_t *edge_index_dev, int64_t num_edges, int32_t num_nodes,
-                                  int32_t tile_nodes, void *stream, tecgat_plan_t **plan_out) {
+                                  int32_t tile_nodes_fwd, int32_t tile_nodes_bwd, void *stream, tecgat_plan_t **plan_out) {
     TG_REQUIRE(plan_out != nullptr, TECGAT_EINVAL, "plan_create: plan_out is NULL");
     *plan_out = nullptr;
     TG_REQUIRE(num_nodes > 0, TECGAT_EINVAL, "plan_create: num_nodes must be positive (got %d)", num_nodes);
     TG_REQUIRE(num_edges >= 0, TECGAT_EINVAL, "plan_create: negative edge count");
     TG_REQUIRE(num_edges == 0 || edge_index_dev != nullptr, TECGAT_EINVAL, "plan_create: edge_index is NULL");
-    TG_REQUIRE(tile_nodes >= 8 && tile_nodes <= 1024, TECGAT_EINVAL, "plan_create: tile_nodes %d outside [8, 1024]",
-               tile_nodes);
+    for (int32_t t : {tile_nodes_fwd, tile_nodes_bwd})
+        TG_REQUIRE(t >= 1 && t <= 512, TECGAT_EINVAL, "plan_create: tile_nodes %d outside [1, 512]", t);
     TG_REQUIRE(num_edges + num_nodes < (int64_t(1) << 31), TECGAT_ENOSUP, "plan_create: more than 2^31 edges");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int64_t N = num_nodes, E0 = num_edges;
@@ -87,12 +172,11 @@ extern "C" int tecgat_plan_create(const int64_t *edge_index_dev, int64_t num_edg
     TG_REQUIRE(p != nullptr, TECGAT_ENOMEM, "plan_create: out of host memory");
     cudaGetDevice(&p->device);
     p->num_nodes = num_nodes;
-    p->tile_nodes = tile_nodes;
-    p->num_tiles = static_cast<int32_t>((N + tile_nodes - 1) / tile_nodes);
     p->num_edges = E;
     p->kept_edges = kept;
 
-    // ---- destination-sorted CSR (stable counting sort; self loop appended last per row) ----------
+    // ---- both CSR orientations (stable counting sort; every row STARTS with the node's self loop, then the kept
+    //      edges in input order).  The self loop's score is the softmax shift of the row (edge_fwd.cu). -------------
     std::vector<int32_t> rp_in(N + 1, 0), rp_out(N + 1, 0);
     for (int64_t e = 0; e < E0; ++e)
         if (src[e] != dst[e]) {
@@ -113,6 +197,15 @@ extern "C" int tecgat_plan_create(const int64_t *edge_index_dev, int64_t num_edg
     {
         std::vector<int32_t> cur_in(rp_in.begin(), rp_in.end() - 1), cur_out(rp_out.begin(), rp_out.end() - 1);
         std::vector<int32_t> slot_of_edge(E);  // PyG edge id -> in-CSR slot
+        for (int64_t i = 0; i < N; ++i) {
+            const int32_t k = cur_in[i]++;
+            col_in[k] = static_cast<int32_t>(i);
+            eid_in[k] = static_cast<int32_t>(kept + i);  // PyG appends the self loops after the kept edges
+            slot_of_edge[kept + i] = k;
+            const int32_t k2 = cur_out[i]++;
+            col_out[k2] = static_cast<int32_t>(i);
+            slot_out[k2] = k;
+        }
         int32_t id = 0;
         for (int64_t e = 0; e < E0; ++e)
             if (src[e] != dst[e]) {
@@ -122,12 +215,6 @@ extern "C" int tecgat_plan_create(const int64_t *edge_index_dev, int64_t num_edg
                 slot_of_edge[id] = k;
                 ++id;
             }
-        for (int64_t i = 0; i < N; ++i) {
-            const int32_t k = cur_in[i]++;
-            col_in[k] = static_cast<int32_t>(i);
-            eid_in[k] = static_cast<int32_t>(kept + i);
-            slot_of_edge[kept + i] = k;
-        }
         id = 0;
         for (int64_t e = 0; e < E0; ++e)
             if (src[e] != dst[e]) {
@@ -136,35 +223,14 @@ extern "C" int tecgat_plan_create(const int64_t *edge_index_dev, int64_t num_edg
                 slot_out[k2] = slot_of_edge[id];
                 ++id;
             }
-        for (int64_t i = 0; i < N; ++i) {
-            const int32_t k2 = cur_out[i]++;
-            col_out[k2] = static_cast<int32_t>(i);
-            slot_out[k2] = slot_of_edge[kept + i];
-        }
-    }
-    // ---- per-tile row windows ------------------------------------------------------------------------
-    std::vector<int32_t> lo(p->num_tiles), hi(p->num_tiles);
-    for (int32_t t = 0; t < p->num_tiles; ++t) {
-        const int64_t n0 = int64_t(t) * tile_nodes, n1 = std::min<int64_t>(N, n0 + tile_nodes);
-        int32_t l = static_cast<int32_t>(n0), h = static_cast<int32_t>(n1 - 1);
-        for (int32_t k = rp_in[n0]; k < rp_in[n1]; ++k) {
-            l = std::min(l, col_in[k]);
-            h = std::max(h, col_in[k]);
-        }
-        for (int32_t k = rp_out[n0]; k < rp_out[n1]; ++k) {
-            l = std::min(l, col_out[k]);
-            h = std::max(h, col_out[k]);
-        }
-        lo[t] = l;
-        hi[t] = h + 1;
-        p->max_window = std::max(p->max_window, h + 1 - l);
     }
 
     int rc = TECGAT_OK;
     if ((rc = upload(&p->rowptr_in, rp_in, st)) || (rc = upload(&p->col_in, col_in, st)) ||
         (rc = upload(&p->rowptr_out, rp_out, st)) || (rc = upload(&p->col_out, col_out, st)) ||
-        (rc = upload(&p->slot_out, slot_out, st)) || (rc = upload(&p->tile_lo, lo, st)) ||
-        (rc = upload(&p->tile_hi, hi, st))) {
+        (rc = upload(&p->slot_out, slot_out, st)) ||
+        (rc = build_tiling(p->fwd, false, tile_nodes_fwd, N, rp_in, col_in, rp_out, col_out, slot_out, st)) ||
+        (rc = build_tiling(p->bwd, true, tile_nodes_bwd, N, rp_in, col_in, rp_out, col_out, slot_out, st))) {
         tecgat_plan_destroy(p);
         return rc;
     }
@@ -195,11 +261,15 @@ extern "C" int tecgat_plan_info(const tecgat_plan_t *p, int64_t *info) {
     info[0] = p->num_edges;
     info[1] = p->max_in_deg;
     info[2] = p->max_out_deg;
-    info[3] = p->num_tiles;
-    info[4] = p->tile_nodes;
-    info[5] = p->max_window;
+    info[3] = p->fwd.num_tiles;
+    info[4] = p->fwd.T;
+    info[5] = p->fwd.max_window;
     info[6] = p->num_nodes;
     info[7] = p->kept_edges;
+    info[8] = p->bwd.num_tiles;
+    info[9] = p->bwd.T;
+    info[10] = p->bwd.max_window;
+    info[11] = 0;
     return TECGAT_OK;
 }
 
@@ -218,9 +288,9 @@ extern "C" int tecgat_dropout_mask_host(uint64_t seed, int64_t first_slot, int64
     const uint32_t thr = tg::dropout_threshold(dropout_p);
     for (int64_t i = 0; i < count; ++i) {
         const int64_t g = first_slot + i;
-        const uint32_t key = tg::dropout_snapshot_key(seed, uint32_t(g / edges_per_snapshot));
-        const uint32_t slot = uint32_t(g % edges_per_snapshot);
-        for (int32_t h = 0; h < heads; ++h) keep[i * heads + h] = tg::dropout_bits16(key, slot, uint32_t(h)) >= thr;
+        const uint32_t snap = uint32_t(g / edges_per_snapshot), slot = uint32_t(g % edges_per_snapshot);
+        for (int32_t h = 0; h < heads; ++h)
+            keep[i * heads + h] = tg::dropout_bits(tg::dropout_key(seed, snap, uint32_t(h)), slot) >= thr;
     }
     return TECGAT_OK;
 }

@@ -33,12 +33,20 @@ def _stream(device: torch.device):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
-def tile_nodes_for(heads: int) -> int:
-    """Destination nodes per CTA: one lane per (node, head), at most 256 lanes."""
+def tile_nodes_for(heads: int, backward: bool = False) -> int:
+    """Destination nodes per tile of the persistent edge kernels: one lane per (node, head), heads padded to a power
+    of two.  CTA = consumer warps + one producer warp, sized to a multiple of 128 threads (the register-file
+    allocation granule): 15 consumer warps forward (512 threads), 7 backward (256 threads: shared-memory bound)."""
     if heads < 1 or heads > 32:
         raise ValueError(f"heads={heads} unsupported (1..32)")
-    t = 256 // heads
-    return max(8, min(128, (t // 8) * 8))
+    hp = 1
+    while hp < heads:
+        hp *= 2
+    npw = 32 // hp  # nodes per warp
+    warps = 7 if backward else 15
+    knob = os.environ.get("TECGAT_TILE_BWD" if backward else "TECGAT_TILE_FWD")  # tuning knob (benchmarks only)
+    t = int(knob) if knob else warps * npw
+    return max(npw, min(warps * npw, (t // npw) * npw))
 
 
 # Optional per-phase instrumentation used by bench.py: when set to a list, a CUDA event is recorded on the launching
@@ -63,7 +71,7 @@ class GraphPlan:
     """Immutable device-side plan of one ``edge_index`` (see csrc/plan.cu).  Replaces the per-forward
     ``remove_self_loops``/``add_self_loops`` of PyG with a one-time build."""
 
-    def __init__(self, edge_index: torch.Tensor, num_nodes: int, tile_nodes: int):
+    def __init__(self, edge_index: torch.Tensor, num_nodes: int, tile_nodes: int, tile_nodes_bwd: Optional[int] = None):
         if not edge_index.is_cuda:
             raise RuntimeError("tec_mollm_b200: edge_index must be a CUDA tensor (no CPU path)")
         if edge_index.dim() != 2 or edge_index.size(0) != 2 or edge_index.dtype != torch.int64:
@@ -72,15 +80,16 @@ class GraphPlan:
         self.device = ei.device
         self.num_nodes = int(num_nodes)
         self.tile_nodes = int(tile_nodes)
+        self.tile_nodes_bwd = int(tile_nodes_bwd if tile_nodes_bwd is not None else tile_nodes)
         handle = C.c_void_p()
         with torch.cuda.device(self.device):
-            _lib.call("tecgat_plan_create", _ptr(ei), ei.size(1), self.num_nodes, self.tile_nodes,
+            _lib.call("tecgat_plan_create", _ptr(ei), ei.size(1), self.num_nodes, self.tile_nodes, self.tile_nodes_bwd,
                       _stream(self.device), C.byref(handle))
         self._h = handle
-        info = (C.c_int64 * 8)()
+        info = (C.c_int64 * 12)()
         _lib.call("tecgat_plan_info", self._h, info)
         (self.num_edges, self.max_in_degree, self.max_out_degree, self.num_tiles, _, self.max_window, _,
-         self.kept_edges) = [int(v) for v in info]
+         self.kept_edges, self.num_tiles_bwd, _, self.max_window_bwd, _) = [int(v) for v in info]
 
     @property
     def handle(self):
@@ -108,7 +117,7 @@ class GraphPlan:
 
 class _GATv2Function(torch.autograd.Function):
     """forward = project_fwd + edge_fwd; backward = edge_bwd + project_bwd (four launches + two tiny
-    fixed-order reductions).  Saved for backward: x, xl, xr, y, m, den (PyG saves 4-6 (S*E, H, C) tensors)."""
+    fixed-order reductions).  Saved for backward: x, xl, xr, y, stat (PyG saves 4-6 (S*E, H, C) tensors)."""
 
     @staticmethod
     def forward(ctx, x2d, wl, bl, wr, br, att, bias, plan: GraphPlan, S, H, Cc, slope, p, seed, mode, dtype, impl):
@@ -121,23 +130,22 @@ class _GATv2Function(torch.autograd.Function):
             xl = torch.empty((R, HC), device=dev, dtype=st_dtype)
             xr = torch.empty((R, HC), device=dev, dtype=st_dtype)
             y = torch.empty((R, HC), device=dev, dtype=torch.float32)
-            m = torch.empty((R, H), device=dev, dtype=torch.float32)
-            den = torch.empty((R, H), device=dev, dtype=torch.float32)
+            stat = torch.empty((R, H), device=dev, dtype=torch.float32)
             _mark("start_fwd", dev)
             _lib.call("tecgat_project_fwd", _ptr(x2d), _ptr(wl), _ptr(bl), _ptr(wr), _ptr(br), _ptr(xl), _ptr(xr),
                       R, F, HC, dtype, impl, stream)
             _mark("proj_fwd", dev)
-            _lib.call("tecgat_edge_fwd", plan.handle, _ptr(xl), _ptr(xr), _ptr(att), _ptr(bias), _ptr(y), _ptr(m),
-                      _ptr(den), S, H, Cc, slope, p, seed, mode, dtype, stream)
+            _lib.call("tecgat_edge_fwd", plan.handle, _ptr(xl), _ptr(xr), _ptr(att), _ptr(bias), _ptr(y), _ptr(stat),
+                      S, H, Cc, slope, p, seed, mode, dtype, stream)
             _mark("edge_fwd", dev)
-        ctx.save_for_backward(x2d, wl, wr, att, bias, xl, xr, y, m, den)
+        ctx.save_for_backward(x2d, wl, wr, att, bias, xl, xr, y, stat)
         ctx.plan = plan
         ctx.cfg = (S, H, Cc, slope, p, seed, mode, dtype, impl)
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        x2d, wl, wr, att, bias, xl, xr, y, m, den = ctx.saved_tensors
+        x2d, wl, wr, att, bias, xl, xr, y, stat = ctx.saved_tensors
         S, H, Cc, slope, p, seed, mode, dtype, impl = ctx.cfg
         plan: GraphPlan = ctx.plan
         dev = x2d.device
@@ -146,6 +154,8 @@ class _GATv2Function(torch.autograd.Function):
         gy = gy.contiguous()
         if gy.dtype != torch.float32:
             gy = gy.float()
+        if gy.data_ptr() % 16:  # bulk-TMA sources are 16-byte aligned
+            gy = gy.clone()
         with torch.cuda.device(dev):  # autograd worker threads do not inherit the current device
             stream = _stream(dev)
             dxl = torch.empty_like(xl)
@@ -162,8 +172,8 @@ class _GATv2Function(torch.autograd.Function):
             ws2 = torch.empty((max(1, _lib.lib().tecgat_project_bwd_workspace(R, F, HC, impl)),), device=dev,
                               dtype=torch.uint8)
             _mark("start_bwd", dev)
-            _lib.call("tecgat_edge_bwd", plan.handle, _ptr(xl), _ptr(xr), _ptr(att), _ptr(bias), _ptr(y), _ptr(m),
-                      _ptr(den), _ptr(gy), _ptr(dxl), _ptr(dxr), _ptr(datt), _ptr(dbias), _ptr(ws1), S, H, Cc, slope, p,
+            _lib.call("tecgat_edge_bwd", plan.handle, _ptr(xl), _ptr(xr), _ptr(att), _ptr(bias), _ptr(y), _ptr(stat),
+                      _ptr(gy), _ptr(dxl), _ptr(dxr), _ptr(datt), _ptr(dbias), _ptr(ws1), S, H, Cc, slope, p,
                       seed, mode, dtype, stream)
             _mark("edge_bwd", dev)
             _lib.call("tecgat_project_bwd", _ptr(dxl), _ptr(dxr), _ptr(x2d), _ptr(wl), _ptr(wr), _ptr(dx), _ptr(dwl),
@@ -227,6 +237,7 @@ class GATv2Conv(nn.Module):
         self.bias = nn.Parameter(torch.empty(heads * out_channels))
         self._plans = {}
         self._tile_nodes = tile_nodes_for(heads)
+        self._tile_nodes_bwd = tile_nodes_for(heads, backward=True)
         self.reset_parameters()
 
     def __getstate__(self):  # graph plans hold device handles: never pickled / deep-copied
@@ -248,7 +259,7 @@ class GATv2Conv(nn.Module):
         hit = self._plans.get(key)
         if hit is not None:
             return hit[0]
-        plan = GraphPlan(edge_index, num_nodes, self._tile_nodes)
+        plan = GraphPlan(edge_index, num_nodes, self._tile_nodes, self._tile_nodes_bwd)
         if len(self._plans) >= 8:
             self._plans.pop(next(iter(self._plans)))
         self._plans[key] = (plan, edge_index)  # keep the tensor alive so its data_ptr cannot be recycled

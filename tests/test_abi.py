@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol(lib):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/tecgat.h but not exported"
     assert sorted(_lib.EXPORTED_SYMBOLS) == names, "ctypes signature table and header disagree"
-    assert lib.tecgat_abi_version() == 1
+    assert lib.tecgat_abi_version() == 2
 
 
 def test_library_is_sm100a_native(lib):
@@ -83,7 +83,7 @@ def test_errors_are_reported_not_thrown(lib):
 
     with pytest.raises(RuntimeError, match="bad argument"):
         _lib.call("tecgat_dropout_mask_host", C.c_uint64(0), 0, 10, 0, C.c_float(0.1), 5, None)
-    info = (C.c_int64 * 8)()
+    info = (C.c_int64 * 12)()
     assert lib.tecgat_plan_info(None, info) != 0
     assert b"NULL" in lib.tecgat_last_error()
 

@@ -84,8 +84,8 @@ def test_plan_matches_pyg_edge_surgery(cuda_device):
         ids = eid[rowptr[i]:rowptr[i + 1]]
         assert np.all(dst[ids] == i)                                  # destination-sorted
         assert np.array_equal(col[rowptr[i]:rowptr[i + 1]], src[ids])
-        assert np.all(np.diff(ids) > 0)                               # stable: PyG's per-destination order
-        assert ids[-1] == plan.kept_edges + i                         # the self loop is last
+        assert ids[0] == plan.kept_edges + i                          # every row starts with its self loop ...
+        assert np.all(np.diff(ids[1:]) > 0)                           # ... then the kept edges in PyG's (stable) order
     assert plan.max_in_degree == int(np.diff(rowptr).max())
 
 
