@@ -1,4 +1,6 @@
 // project.cu -- C ABI of the lin_l / lin_r projections: argument checks + implementation choice.
+#include <cstdlib>
+
 #include "project.cuh"
 
 extern "C" int tecgat_project_fwd(const float *x, const float *wl, const float *bl, const float *wr, const float *br,
@@ -18,7 +20,9 @@ extern "C" int tecgat_project_fwd(const float *x, const float *wl, const float *
 
 extern "C" int64_t tecgat_project_bwd_workspace(int64_t rows, int32_t F, int32_t hc, int32_t impl) {
     if (rows <= 0 || F <= 0 || hc <= 0) return 0;
-    return impl == TECGAT_PROJ_FFMA ? tg::project_bwd_ffma_workspace(rows, F, hc) : tg::project_bwd_tc_workspace(rows, F, hc);
+    if (impl == TECGAT_PROJ_FFMA) return tg::project_bwd_ffma_workspace(rows, F, hc);
+    const int64_t a = tg::project_bwd_tc_workspace(rows, F, hc), b = tg::project_bwd_rt_workspace(rows, F, hc);
+    return a > b ? a : b;
 }
 
 extern "C" int tecgat_project_bwd(const void *dxl, const void *dxr, const float *x, const float *wl, const float *wr,
@@ -31,5 +35,11 @@ extern "C" int tecgat_project_bwd(const void *dxl, const void *dxr, const float 
     if (impl == TECGAT_PROJ_FFMA)
         return tg::project_bwd_ffma(dxl, dxr, x, wl, wr, dx, dwl, dbl, dwr, dbr, workspace, rows, F, hc, dtype, st);
     TG_REQUIRE(impl == TECGAT_PROJ_TC, TECGAT_EINVAL, "project_bwd: bad impl %d", impl);
+    // Product path: the register-tiled packed-fp32 kernel (project_bwd_rt.cu explains why the backward is not on tcgen05);
+    // TECGAT_PROJ_BWD=tc selects the tcgen05 kernel (kept for the bf16 contract experiments and as a cross-check).
+    const char *env = getenv("TECGAT_PROJ_BWD");
+    const bool force_tc = env && env[0] == 't';
+    if (!force_tc && tg::project_bwd_rt_supported(F, hc, dxl, dxr, x, dx))
+        return tg::project_bwd_rt(dxl, dxr, x, wl, wr, dx, dwl, dbl, dwr, dbr, workspace, rows, F, hc, dtype, st);
     return tg::project_bwd_tc(dxl, dxr, x, wl, wr, dx, dwl, dbl, dwr, dbr, workspace, rows, F, hc, dtype, st);
 }

@@ -18,4 +18,9 @@ int64_t project_bwd_tc_workspace(int64_t R, int F, int HC);
 int project_bwd_tc(const void *dxl, const void *dxr, const float *x, const float *wl, const float *wr, float *dx,
                    float *dwl, float *dbl, float *dwr, float *dbr, void *workspace, int64_t R, int F, int HC, int dtype,
                    cudaStream_t st);
+// register-tiled FFMA2 backward (project_bwd_rt.cu): the product path of the backward projection
+bool project_bwd_rt_supported(int F, int HC, const void *dxl, const void *dxr, const void *x, const void *dx);
+int64_t project_bwd_rt_workspace(int64_t R, int F, int HC);
+int project_bwd_rt(const void *dxl, const void *dxr, const float *x, const float *wl, const float *wr, float *dx, float *dwl,
+                   float *dbl, float *dwr, float *dbr, void *workspace, int64_t R, int F, int HC, int dtype, cudaStream_t st);
 }  // namespace tg

@@ -1,0 +1,326 @@
+// project_bwd_rt.cu -- backward of the lin_l / lin_r projections on the packed fp32 pipe, register tiled:
+//     dx = dxl Wl + dxr Wr            (rows x 2HC) . (2HC x F)
+//     dWl = dxl^T x, dbl = sum dxl    (same for r)                     one pass over dxl, dxr, x
+// Why not tensor cores here: both GEMMs have K or N = 22..44; the fp32 contract (1e-5) needs every operand split into
+// 3xTF32 / 3xbf16 terms AND re-laid into the UMMA core-matrix layout by CUDA cores, and the weight-gradient GEMM reduces
+// over ROWS, i.e. wants MN-major operands that tcgen05 only takes for 16-bit types.  That re-layout costs more issue
+// slots than the 2,000 FMAs per row it would off-load (measured: 4.4 ms for the tcgen05 version of this kernel at B=128,
+// against a 0.96 ms HBM floor).  The forward projection, whose only large operand is x, stays on tcgen05 (project_tc.cu).
+//
+// Persistent CTA = 16 warps: one bulk-TMA producer warp streaming 128-row tiles of (dxl, dxr, x) through a 5-stage
+// mbarrier ring, and three TEAMS of five consumer warps; team t owns tiles t, t+3, ..  Inside a team
+//   * 2 "dx" warps: thread = 4 rows x 12 outputs; per pair of gradient columns 4 x LDS.64 (rows) + 6 x LDS.128 (weights,
+//     broadcast) feed 48 FFMA2; the tile leaves through shared memory as one bulk-TMA store;
+//   * 3 "dW" warps: thread = (16-row slice, 8 gradient columns, 12 input columns): 10 x LDS.64 feed 48 FFMA2 per row;
+//     its 96 fp32 accumulators live in registers for the whole kernel (column 23 of the padded x tile is a constant 1:
+//     the bias gradients come out of the same accumulators).
+// End of kernel: the 24 (team, slice) partials are summed in fp64 in a fixed order -> one partial row per CTA, then the
+// fixed-order fp64 second stage (reduce.cu).  Deterministic, no atomics.
+#include <type_traits>
+
+#include "common.cuh"
+#include "project.cuh"
+#include "reduce.cuh"
+
+namespace tg {
+
+namespace rt {
+constexpr int kRows = 128;   // rows per tile
+constexpr int kFP = 24;      // padded input channels (F <= 22: column 23 carries the constant 1)
+constexpr int kHP = 24;      // padded gradient columns per array (HC <= 24)
+constexpr int kTeams = 3, kTeamWarps = 5, kStages = 5;
+constexpr int kConsumers = kTeams * kTeamWarps * 32;
+constexpr int kThreads = kConsumers + 32;
+constexpr int kSlices = 8;   // 16-row slices of a tile (dW warps)
+constexpr int kPad = 128;    // zeroed bytes after every staged tile (threads read up to 2 elements past a row)
+
+struct Args {
+    const void *dxl, *dxr;
+    const float *x, *wl, *wr;
+    float *dx;        // may be NULL
+    float *partials;  // (grid, 2*HC*F + 2*HC): [dWl | dWr | dbl | dbr] per CTA
+    int64_t R;
+    int32_t F, HC;
+};
+
+struct Smem {
+    uint32_t bars, w, stage0, stage_bytes, off_dr, off_x, dxst, dxst_bytes, total;
+};
+template <typename ST>
+__host__ __device__ inline Smem layout(int F, int HC) {
+    Smem s;
+    uint32_t o = 0;
+    s.bars = o; o += 128;
+    s.w = o; o += 2 * kHP * kFP * 4;
+    o = (o + 127) & ~127u;
+    const uint32_t tile_d = ((kRows * HC * (uint32_t)sizeof(ST) + kPad + 127) / 128) * 128;
+    const uint32_t tile_x = ((kRows * F * 4u + kPad + 127) / 128) * 128;
+    s.off_dr = tile_d;
+    s.off_x = 2 * tile_d;
+    s.stage_bytes = 2 * tile_d + tile_x;
+    s.stage0 = o; o += kStages * s.stage_bytes;
+    s.dxst_bytes = ((kRows * F * 4u + 127) / 128) * 128;
+    s.dxst = o; o += kTeams * s.dxst_bytes;
+    s.total = o;
+    return s;
+}
+
+__device__ __forceinline__ float2 ld_pair(const float *p) { return *reinterpret_cast<const float2 *>(p); }
+__device__ __forceinline__ float2 ld_pair(const __nv_bfloat16 *p) {
+    const uint32_t u = *reinterpret_cast<const uint32_t *>(p);
+    return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xFFFF0000u));
+}
+__device__ __forceinline__ void named_bar(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
+template <typename ST>
+__global__ void __launch_bounds__(kThreads, 1) project_bwd_rt_kernel(const Args a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int F = a.F, HC = a.HC;
+    const Smem L = layout<ST>(F, HC);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + L.bars), *empty = full + kStages;
+    float *W_s = reinterpret_cast<float *>(smem + L.w);  // [2][kHP][kFP], zero padded
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t num_tiles = (a.R + kRows - 1) / kRows;
+    const int n_local = blockIdx.x < num_tiles ? (int)((num_tiles - 1 - blockIdx.x) / gridDim.x) + 1 : 0;
+    const bool need_dx = a.dx != nullptr;
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kTeamWarps);
+        }
+        fence_mbar_init();
+    }
+    for (int i = tid; i < 2 * kHP * kFP; i += kThreads) {
+        const int arr = i / (kHP * kFP), c = (i / kFP) % kHP, f = i % kFP;
+        float v = 0.f;
+        if (c < HC && f < F) {
+            v = (arr ? a.wr : a.wl)[c * F + f];
+            if (std::is_same<ST, __nv_bfloat16>::value) v = __bfloat162float(__float2bfloat16_rn(v));  // autocast rounds W
+        }
+        W_s[i] = v;
+    }
+    for (int i = tid; i < kStages * (int)(L.stage_bytes / 4); i += kThreads) reinterpret_cast<uint32_t *>(smem + L.stage0)[i] = 0u;
+    fence_proxy_async();
+    __syncthreads();
+
+    if (warp == kTeams * kTeamWarps) {
+        // ================================ producer warp ================================
+        if (lane == 0) {
+            for (int it = 0; it < n_local; ++it) {
+                const int s = it % kStages;
+                if (it >= kStages) mbar_wait(&empty[s], ((it / kStages) - 1) & 1);
+                const int64_t tile = blockIdx.x + (int64_t)it * gridDim.x, r0 = tile * kRows;
+                const int nr = (int)((a.R - r0) < (int64_t)kRows ? (a.R - r0) : (int64_t)kRows);
+                unsigned char *st = smem + L.stage0 + (size_t)s * L.stage_bytes;
+                const uint32_t bd = (uint32_t)nr * HC * (uint32_t)sizeof(ST), bx = (uint32_t)nr * F * 4u;
+                const unsigned char *srcs[3] = {reinterpret_cast<const unsigned char *>(static_cast<const ST *>(a.dxl) + r0 * HC),
+                                                reinterpret_cast<const unsigned char *>(static_cast<const ST *>(a.dxr) + r0 * HC),
+                                                reinterpret_cast<const unsigned char *>(a.x + r0 * F)};
+                unsigned char *dsts[3] = {st, st + L.off_dr, st + L.off_x};
+                const uint32_t lens[3] = {bd, bd, bx};
+                uint32_t tx = 0;
+                for (int q = 0; q < 3; ++q) {  // <16-byte ragged ends (last tile only): plain 2-byte copies
+                    const uint32_t mid = lens[q] & ~15u;
+                    for (uint32_t b = mid; b < lens[q]; b += 2)
+                        *reinterpret_cast<uint16_t *>(dsts[q] + b) = *reinterpret_cast<const uint16_t *>(srcs[q] + b);
+                    tx += mid;
+                }
+                mbar_arrive_expect_tx(&full[s], tx);
+                for (int q = 0; q < 3; ++q) {
+                    const uint32_t mid = lens[q] & ~15u;
+                    if (mid) bulk_g2s(dsts[q], srcs[q], mid, &full[s]);
+                }
+            }
+        }
+        return;
+    }
+
+    // ================================ consumer teams ================================
+    const int team = warp / kTeamWarps, tw = warp % kTeamWarps;
+    const int HCe = (HC + 1) & ~1;
+    double *red = reinterpret_cast<double *>(smem + L.stage0);  // end of kernel: [2*kHP][kFP] fp64 sums (the ring is free by then)
+
+    if (tw < 2) {
+        // -------- dx warps: thread = rows {lane, lane+32, lane+64, lane+96} x outputs 12u .. 12u+11 ------------------------
+        const int u = tw;
+        float *dxst = reinterpret_cast<float *>(smem + L.dxst + (size_t)team * L.dxst_bytes);
+        for (int it = team; it < n_local; it += kTeams) {
+            const int s = it % kStages;
+            const int64_t tile = blockIdx.x + (int64_t)it * gridDim.x, r0 = tile * kRows;
+            const int nr = (int)((a.R - r0) < (int64_t)kRows ? (a.R - r0) : (int64_t)kRows);
+            const unsigned char *st = smem + L.stage0 + (size_t)s * L.stage_bytes;
+            mbar_wait(&full[s], (it / kStages) & 1);
+            if (!need_dx) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[s]);
+                continue;
+            }
+            float2 o[4][6];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int k = 0; k < 6; ++k) o[i][k] = make_float2(0.f, 0.f);
+#pragma unroll 1
+            for (int arr = 0; arr < 2; ++arr) {
+                const ST *d = reinterpret_cast<const ST *>(st + (arr ? L.off_dr : 0u)) + lane * HC;
+                const float *w = W_s + arr * kHP * kFP + 12 * u;
+#pragma unroll 2
+                for (int c = 0; c < HCe; c += 2) {
+                    float2 dv[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) dv[i] = ld_pair(d + 32 * i * HC + c);
+                    float4 w0[3], w1[3];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        w0[k] = *reinterpret_cast<const float4 *>(w + c * kFP + 4 * k);
+                        w1[k] = *reinterpret_cast<const float4 *>(w + (c + 1) * kFP + 4 * k);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float2 a0 = make_float2(dv[i].x, dv[i].x), a1 = make_float2(dv[i].y, dv[i].y);
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            o[i][2 * k] = __ffma2_rn(a0, make_float2(w0[k].x, w0[k].y), o[i][2 * k]);
+                            o[i][2 * k + 1] = __ffma2_rn(a0, make_float2(w0[k].z, w0[k].w), o[i][2 * k + 1]);
+                            o[i][2 * k] = __ffma2_rn(a1, make_float2(w1[k].x, w1[k].y), o[i][2 * k]);
+                            o[i][2 * k + 1] = __ffma2_rn(a1, make_float2(w1[k].z, w1[k].w), o[i][2 * k + 1]);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+            if (tw == 0 && lane == 0) bulk_wait_read0();  // the previous tile's bulk store has drained dxst
+            named_bar(1 + team, 64);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    const int f = 12 * u + 2 * k;
+                    if (f < F) *reinterpret_cast<float2 *>(dxst + (lane + 32 * i) * F + f) = o[i][k];
+                }
+            fence_proxy_async();
+            named_bar(1 + team, 64);
+            float *gdx = a.dx + r0 * F;
+            if (nr == kRows) {
+                if (tw == 0 && lane == 0) {
+                    bulk_s2g(gdx, dxst, kRows * F * 4u);
+                    bulk_commit();
+                }
+            } else {
+                for (int i = tw * 32 + lane; i < nr * F; i += 64) gdx[i] = dxst[i];
+            }
+        }
+        if (need_dx && tw == 0 && lane == 0) bulk_wait0();
+        named_bar(8, kConsumers);  // all tiles consumed: the ring is free
+        for (int i = tid; i < 2 * kHP * kFP; i += kConsumers) red[i] = 0.0;
+        for (int g = 0; g <= kTeams * kSlices; ++g) named_bar(8, kConsumers);
+    } else {
+        // -------- dW warps: thread = (16-row slice, gradient columns 8 ot .. 8 ot+7, input columns 12 u .. 12 u+11) -------------
+        const int q = (tw - 2) * 32 + lane;  // 0 .. 95
+        const int slice = q / 12, ot = (q % 12) >> 1, u = q & 1;
+        float2 acc[8][6];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int k = 0; k < 6; ++k) acc[i][k] = make_float2(0.f, 0.f);
+        const uint32_t d_off = (ot < 3 ? 0u : L.off_dr) + (uint32_t)(8 * (ot < 3 ? ot : ot - 3)) * (uint32_t)sizeof(ST);
+        for (int it = team; it < n_local; it += kTeams) {
+            const int s = it % kStages;
+            const int64_t r0 = (blockIdx.x + (int64_t)it * gridDim.x) * kRows;
+            const int nr = (int)((a.R - r0) < (int64_t)kRows ? (a.R - r0) : (int64_t)kRows);
+            const unsigned char *st = smem + L.stage0 + (size_t)s * L.stage_bytes;
+            const ST *d = reinterpret_cast<const ST *>(st + d_off);
+            const float *xp = reinterpret_cast<const float *>(st + L.off_x) + 12 * u;
+            const int rbeg = slice * (kRows / kSlices), rend = min(nr, rbeg + kRows / kSlices);
+            mbar_wait(&full[s], (it / kStages) & 1);
+#pragma unroll 1
+            for (int r = rbeg; r < rend; ++r) {
+                float2 dv[4], xv[6];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dv[i] = ld_pair(d + r * HC + 2 * i);
+#pragma unroll
+                for (int k = 0; k < 6; ++k) xv[k] = ld_pair(xp + r * F + 2 * k);
+                if (u) xv[5].y = 1.f;  // column 23: the constant 1 of the bias gradient
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 a0 = make_float2(dv[i].x, dv[i].x), a1 = make_float2(dv[i].y, dv[i].y);
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) {
+                        acc[2 * i][k] = __ffma2_rn(a0, xv[k], acc[2 * i][k]);
+                        acc[2 * i + 1][k] = __ffma2_rn(a1, xv[k], acc[2 * i + 1][k]);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
+        // ---- CTA partial: the 24 (team, slice) register partials summed in fp64, fixed order ----------------------------
+        named_bar(8, kConsumers);
+        for (int i = tid; i < 2 * kHP * kFP; i += kConsumers) red[i] = 0.0;
+        named_bar(8, kConsumers);
+        for (int g = 0; g < kTeams * kSlices; ++g) {
+            if (team * kSlices + slice == g) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) {
+                        double *p = red + (8 * ot + i) * kFP + 12 * u + 2 * k;
+                        p[0] += (double)acc[i][k].x;
+                        p[1] += (double)acc[i][k].y;
+                    }
+            }
+            named_bar(8, kConsumers);
+        }
+    }
+    const int O = 2 * HC;
+    float *out = a.partials + (int64_t)blockIdx.x * (O * F + O);
+    for (int i = tid; i < O * F + O; i += kConsumers) {
+        int o, f;
+        if (i < O * F) { o = i / F; f = i - o * F; } else { o = i - O * F; f = kFP - 1; }
+        const int arr = o >= HC, c = o - arr * HC;
+        out[i] = (float)red[(arr * kHP + c) * kFP + f];
+    }
+}
+
+static int grid_for(int64_t R) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t tiles = (R + kRows - 1) / kRows;
+    return (int)(tiles < sms ? tiles : sms);
+}
+}  // namespace rt
+
+bool project_bwd_rt_supported(int F, int HC, const void *dxl, const void *dxr, const void *x, const void *dx) {
+    const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dxl) | reinterpret_cast<uintptr_t>(dxr) |
+                           reinterpret_cast<uintptr_t>(dx)) & 15) == 0;
+    return aligned && F >= 2 && F <= rt::kFP - 2 && (F % 2) == 0 && HC >= 2 && HC <= rt::kHP && (HC % 2) == 0;
+}
+
+int64_t project_bwd_rt_workspace(int64_t R, int F, int HC) { return int64_t(rt::grid_for(R)) * (2 * HC * F + 2 * HC) * (int64_t)sizeof(float); }
+
+int project_bwd_rt(const void *dxl, const void *dxr, const float *x, const float *wl, const float *wr, float *dx, float *dwl,
+                   float *dbl, float *dwr, float *dbr, void *workspace, int64_t R, int F, int HC, int dtype, cudaStream_t st) {
+    rt::Args a;
+    a.dxl = dxl; a.dxr = dxr; a.x = x; a.wl = wl; a.wr = wr; a.dx = dx; a.partials = static_cast<float *>(workspace);
+    a.R = R; a.F = F; a.HC = HC;
+    const int grid = rt::grid_for(R);
+    if (dtype == TECGAT_F32) {
+        const rt::Smem L = rt::layout<float>(F, HC);
+        auto k = rt::project_bwd_rt_kernel<float>;
+        TG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+        k<<<grid, rt::kThreads, L.total, st>>>(a);
+    } else {
+        const rt::Smem L = rt::layout<__nv_bfloat16>(F, HC);
+        auto k = rt::project_bwd_rt_kernel<__nv_bfloat16>;
+        TG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+        k<<<grid, rt::kThreads, L.total, st>>>(a);
+    }
+    TG_LAUNCH_CHECK();
+    const int O = 2 * HC;
+    ReduceSegs segs = {{dwl, dwr, dbl, dbr}, {0, HC * F, O * F, O * F + HC}, {HC * F, O * F, O * F + HC, O * F + O}};
+    return reduce_columns(a.partials, grid, O * F + O, segs, st);
+}
+
+}  // namespace tg
