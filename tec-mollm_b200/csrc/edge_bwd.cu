@@ -99,11 +99,11 @@ __device__ __forceinline__ float out_score(const CV<C> &attm, float c1, const CV
 // (slots past the degree read a valid row and get weight 0).
 //   NbrIn(k) / NbrOut(k): row index of the k-th in- / out-neighbour relative to the base pointers
 //   SlotOut(k): in-CSR slot (dropout counter) of the k-th out-edge;  DsOf(u, gu): (delta_u, stat_u)
-template <int C, typename ST, bool VEC, class NbrIn, class NbrOut, class SlotOut, class DsOf>
+template <int C, typename ST, bool VEC, class NbrIn, class NbrOut, class SlotOut, class DsOf, class WaitDs>
 __device__ __forceinline__ void bwd_lane(const CV<C> &attp, const CV<C> &attm, const CV<C> &att, float slope, const DropCfg &drop,
                                          const ST *xl_base, const ST *xr_base, const float *g_base, int HC, int par, ptrdiff_t vrow,
                                          float2 dv, int deg_in, int kmax_in, int deg_out, int kmax_out, uint32_t slot0,
-                                         NbrIn nbr_in, NbrOut nbr_out, SlotOut slot_out, DsOf ds_of, bool active, CV<C> &dxl,
+                                         NbrIn nbr_in, NbrOut nbr_out, SlotOut slot_out, DsOf ds_of, WaitDs wait_ds, bool active, CV<C> &dxl,
                                          CV<C> &dxr, CV<C> &tatt, CV<C> &g_v) {
     CV<C> xl_v, xr_v, B_in, B_out, G;
     if (active) {
@@ -150,6 +150,7 @@ __device__ __forceinline__ void bwd_lane(const CV<C> &attp, const CV<C> &attm, c
         acc_step<C>(B_in, sb, db);
     }
     // ---- role 2: v as SOURCE, out-edges (v -> u): A_out, B_out, G = sum alpha q g_u ------------------------------
+    wait_ds();  // the (delta, stat) of every window row has been written (other warps' pre-pass shares)
     const float c1 = cv_dot<C>(attp, xl_v);
 #pragma unroll 1
     for (int k = 1; k < kmax_out; k += 2) {
@@ -198,6 +199,7 @@ __global__ void __launch_bounds__(256, 1) edge_bwd_kernel(const EdgeBwdArgs a) {
     uint64_t *empty = full + kMaxStages;
     uint64_t *yfull = empty + kMaxStages;
     uint64_t *yempty = yfull + 1;
+    uint64_t *dready = yempty + 1;  // per stage: every consumer warp has written its share of the (delta, stat) planes
     const tg_tile_meta *meta_s = reinterpret_cast<const tg_tile_meta *>(smem + a.off_meta);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ncw = (blockDim.x >> 5) - 1;
@@ -210,6 +212,7 @@ __global__ void __launch_bounds__(256, 1) edge_bwd_kernel(const EdgeBwdArgs a) {
         for (int s = 0; s < NS; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], ncw);
+            mbar_init(&dready[s], ncw);
         }
         mbar_init(yfull, 1);
         mbar_init(yempty, ncw);
@@ -335,26 +338,30 @@ __global__ void __launch_bounds__(256, 1) edge_bwd_kernel(const EdgeBwdArgs a) {
             float2 *ds = reinterpret_cast<float2 *>(stage + a.off_ds);  // [head][window row] -> (delta, stat)
             mbar_wait(&full[ring.st], ring.ph);
             mbar_wait(yfull, yph);
-            // ---- pre-pass: delta = g . (y - bias) for the window rows of this lane's head (rows node_l, node_l + T, ..)
-            if (head_ok) {
-                for (int r = node_l; r < win; r += T) {
-                    CV<C> gg, yy;
-                    cv_load<C, VEC>(gg, g_s + r * HC + hh * C, par);
-                    cv_load<C, VEC>(yy, y_s + r * HC + hh * C, par);
-                    float2 d2 = make_float2(0.f, 0.f);
+            // ---- pre-pass: delta = g . (y - bias).  Each lane takes the window rows node_l, node_l + T, .. of its head
+            //      (needed by the SOURCE role of every lane) and its own row (DESTINATION role: no waiting on other warps)
+            auto delta_of = [&](int r) -> float2 {
+                CV<C> gg, yy;
+                cv_load<C, VEC>(gg, g_s + r * HC + hh * C, par);
+                cv_load<C, VEC>(yy, y_s + r * HC + hh * C, par);
+                float2 d2 = make_float2(0.f, 0.f);
 #pragma unroll
-                    for (int q = 0; q < CV<C>::NP; ++q) d2 = __ffma2_rn(gg.p[q], __fadd2_rn(yy.p[q], make_float2(-bias_h.p[q].x, -bias_h.p[q].y)), d2);
-                    float dl = d2.x + d2.y;
-                    if (CV<C>::ODD) dl = fmaf(gg.s, yy.s - bias_h.s, dl);
-                    ds[hh * a.cap_rows + r] = make_float2(dl, stat_s[r * H + hh]);
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(yempty);  // y window may be refilled for the next item
-            yph ^= 1u;
-            bar_sync_named(kBarConsumers, nct);  // delta of every window row is visible to every consumer warp
-
+                for (int q = 0; q < CV<C>::NP; ++q) d2 = __ffma2_rn(gg.p[q], __fadd2_rn(yy.p[q], make_float2(-bias_h.p[q].x, -bias_h.p[q].y)), d2);
+                float dl = d2.x + d2.y;
+                if (CV<C>::ODD) dl = fmaf(gg.s, yy.s - bias_h.s, dl);
+                return make_float2(dl, stat_s[r * H + hh]);
+            };
             const int vl = n0 + node_l - lo;  // own row inside the window
+            const float2 dv = active ? delta_of(vl) : make_float2(0.f, 0.f);
+            if (head_ok)
+                for (int r = node_l; r < win; r += T) ds[hh * a.cap_rows + r] = delta_of(r);
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(yempty);  // y window may be refilled for the next item
+                mbar_arrive(&dready[ring.st]);
+            }
+            yph ^= 1u;
+
             int deg_in = 0, deg_out = 0;
             uint32_t slot0 = 0;
             if (active) {
@@ -366,14 +373,16 @@ __global__ void __launch_bounds__(256, 1) edge_bwd_kernel(const EdgeBwdArgs a) {
             }
             const uint32_t slot_base = (uint32_t)hdr[3];
             const float2 *ds_h = ds + hh * a.cap_rows;
-            const float2 dv = active ? ds_h[vl] : make_float2(0.f, 0.f);
+            uint64_t *dr_bar = &dready[ring.st];
+            const uint32_t dr_ph = ring.ph;
             const int kmax_in = __reduce_max_sync(0xFFFFFFFFu, deg_in), kmax_out = __reduce_max_sync(0xFFFFFFFFu, deg_out);
             bwd_lane<C, ST, VEC>(
                 attp, attm, att_h, a.slope, drop, xl_s + hh * C, xr_s + hh * C, g_s + hh * C, HC, par, (ptrdiff_t)vl, dv, deg_in, kmax_in,
                 deg_out, kmax_out, slot0, [&](int k) -> ptrdiff_t { return (ptrdiff_t)ell_in[k * Ts]; },
                 [&](int k) -> ptrdiff_t { return (ptrdiff_t)ell_out[k * Ts]; },
                 [&](int k) -> uint32_t { return slot_base + (uint32_t)slot_rel[k * Ts]; },
-                [&](ptrdiff_t u, const CV<C> &) -> float2 { return ds_h[u]; }, active, dxl, dxr, tatt, g_v);
+                [&](ptrdiff_t u, const CV<C> &) -> float2 { return ds_h[u]; }, [&]() { mbar_wait(dr_bar, dr_ph); }, active, dxl, dxr, tatt,
+                g_v);
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[ring.st]);
             ring.advance(NS);
@@ -437,7 +446,7 @@ __global__ void __launch_bounds__(256, 1) edge_bwd_kernel(const EdgeBwdArgs a) {
                 attp, attm, att_h, a.slope, drop, xl_snap, xr_snap, g_snap, HC, par, (ptrdiff_t)vsafe, dv, deg_in, kmax_in, deg_out, kmax_out,
                 (uint32_t)k0i, [&](int k) -> ptrdiff_t { return k < deg_in ? (ptrdiff_t)__ldg(a.col_in + k0i + k) : (ptrdiff_t)vsafe; },
                 [&](int k) -> ptrdiff_t { return k < deg_out ? (ptrdiff_t)__ldg(a.col_out + k0o + k) : (ptrdiff_t)vsafe; },
-                [&](int k) -> uint32_t { return k < deg_out ? (uint32_t)__ldg(a.slot_out + k0o + k) : 0u; }, ds_of, active, dxl, dxr, tatt,
+                [&](int k) -> uint32_t { return k < deg_out ? (uint32_t)__ldg(a.slot_out + k0o + k) : 0u; }, ds_of, []() {}, active, dxl, dxr, tatt,
                 g_v);
             if (active) {
                 cv_store<C, VEC>(static_cast<ST *>(a.dxl) + row * HC + hh * C, dxl, par);

@@ -11,7 +11,7 @@
 // mbarrier ring, and three TEAMS of five consumer warps; team t owns tiles t, t+3, ..  Inside a team
 //   * 2 "dx" warps: thread = 4 rows x 12 outputs; per pair of gradient columns 4 x LDS.64 (rows) + 6 x LDS.128 (weights,
 //     broadcast) feed 48 FFMA2; the tile leaves through shared memory as one bulk-TMA store;
-//   * 3 "dW" warps: thread = (16-row slice, 8 gradient columns, 12 input columns): 10 x LDS.64 feed 48 FFMA2 per row;
+//   * 3 "dW" warps: thread = (every 8th row, 8 gradient columns, 12 input columns): 10 x LDS.64 feed 48 FFMA2 per row;
 //     its 96 fp32 accumulators live in registers for the whole kernel (column 23 of the padded x tile is a constant 1:
 //     the bias gradients come out of the same accumulators).
 // End of kernel: the 24 (team, slice) partials are summed in fp64 in a fixed order -> one partial row per CTA, then the
@@ -233,10 +233,9 @@ __global__ void __launch_bounds__(kThreads, 1) project_bwd_rt_kernel(const Args 
             const unsigned char *st = smem + L.stage0 + (size_t)s * L.stage_bytes;
             const ST *d = reinterpret_cast<const ST *>(st + d_off);
             const float *xp = reinterpret_cast<const float *>(st + L.off_x) + 12 * u;
-            const int rbeg = slice * (kRows / kSlices), rend = min(nr, rbeg + kRows / kSlices);
             mbar_wait(&full[s], (it / kStages) & 1);
 #pragma unroll 1
-            for (int r = rbeg; r < rend; ++r) {
+            for (int r = slice; r < nr; r += kSlices) {  // interleaved rows: the slices of a warp hit different banks
                 float2 dv[4], xv[6];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) dv[i] = ld_pair(d + r * HC + 2 * i);
