@@ -108,11 +108,53 @@ __device__ __forceinline__ void write_row_canonical(unsigned char *base_hi, unsi
     }
 }
 
-template <bool BF16>
+// Compile-time F: the row is read with 8-byte loads and every bound folds away (straight-line code).
+template <bool BF16, int FT>
+__device__ __forceinline__ void write_row_canonical_fast(unsigned char *base_hi, unsigned char *base_lo, int r, uint32_t P,
+                                                         const float *xrow) {
+    constexpr int KP = BF16 ? ((FT + 15) / 16) * 16 : ((FT + 7) / 8) * 8;
+    float v[KP];
+#pragma unroll
+    for (int i = 0; i < FT / 2; ++i) {
+        const float2 t = *reinterpret_cast<const float2 *>(xrow + 2 * i);
+        v[2 * i] = t.x;
+        v[2 * i + 1] = t.y;
+    }
+#pragma unroll
+    for (int i = FT; i < KP; ++i) v[i] = 0.f;
+    if constexpr (BF16) {
+#pragma unroll
+        for (int kc = 0; kc < KP / 8; ++kc) {
+            uint32_t w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                __nv_bfloat162 b = __floats2bfloat162_rn(v[kc * 8 + 2 * i], v[kc * 8 + 2 * i + 1]);
+                w[i] = *reinterpret_cast<uint32_t *>(&b);
+            }
+            *reinterpret_cast<uint4 *>(base_hi + canon_off(r, kc, P)) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    } else {
+#pragma unroll
+        for (int kc = 0; kc < KP / 4; ++kc) {
+            float hi[4], lo[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                hi[i] = tf32_rna(v[kc * 4 + i]);
+                lo[i] = v[kc * 4 + i] - hi[i];
+            }
+            *reinterpret_cast<float4 *>(base_hi + canon_off(r, kc, P)) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<float4 *>(base_lo + canon_off(r, kc, P)) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        }
+    }
+}
+
+// FT / HT > 0: compile-time in_channels / heads*out_channels (both even): straight-line worker code; 0: generic.
+template <bool BF16, int FT, int HT>
 __global__ void __launch_bounds__(kTcThreads, 2) project_fwd_tc_kernel(const TcFwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     using ST = typename std::conditional<BF16, __nv_bfloat16, float>::type;
-    const int F = a.F, HC = a.HC, KP = a.KP, NP = a.NP;
+    constexpr bool kFast = FT > 0;
+    const int F = kFast ? FT : a.F, HC = kFast ? HT : a.HC, KP = a.KP, NP = a.NP;
     const int kStages = a.stages;
     const TcFwdSmem L = tc_fwd_smem<BF16>(F, HC, KP, NP, kStages);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bars);
@@ -214,7 +256,8 @@ __global__ void __launch_bounds__(kTcThreads, 2) project_fwd_tc_kernel(const TcF
                 mbar_wait(&x_full[s], (it / kStages) & 1);
                 if (it >= 1) mbar_wait(a_free, (it - 1) & 1);
                 const float *xrow = reinterpret_cast<const float *>(smem + L.xs + s * L.stage_bytes) + row * F;
-                write_row_canonical<BF16>(smem + L.a_hi, smem + L.a_lo, row, L.P_a, F, KP, [&](int k) { return xrow[k]; });
+                if constexpr (kFast) write_row_canonical_fast<BF16, FT>(smem + L.a_hi, smem + L.a_lo, row, L.P_a, xrow);
+                else write_row_canonical<BF16>(smem + L.a_hi, smem + L.a_lo, row, L.P_a, F, KP, [&](int k) { return xrow[k]; });
                 fence_proxy_async();
                 mbar_arrive(a_ready);
                 mbar_arrive(&x_empty[s]);
@@ -229,14 +272,38 @@ __global__ void __launch_bounds__(kTcThreads, 2) project_fwd_tc_kernel(const TcF
                 if (issuer) bulk_wait_read0();   // previous tile's bulk stores have drained the staging buffers
                 named_bar_sync(1, 128);
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * a.acc_stride;
-                for (int cb = 0; cb < NP / 16; ++cb) {
-                    float v[16];
-                    tmem_ld16(taddr + cb * 16, v);
+                if constexpr (kFast) {
+                    constexpr int NPc = ((2 * HT + 15) / 16) * 16;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int n = cb * 16 + i;
-                        if (n < HC) st_elem(out_l + row * HC + n, v[i] + b_s[n]);
-                        else if (n < 2 * HC) st_elem(out_r + row * HC + (n - HC), v[i] + b_s[n]);
+                    for (int cb = 0; cb < NPc / 16; ++cb) {
+                        float v[16];
+                        tmem_ld16(taddr + cb * 16, v);
+#pragma unroll
+                        for (int i = 0; i < 16; i += 2) {  // pairs never straddle the two outputs (HT is even)
+                            const int n = cb * 16 + i;
+                            if (n < 2 * HT) {
+                                ST *dst = n < HT ? out_l + row * HT + n : out_r + row * HT + (n - HT);
+                                const float2 bb = *reinterpret_cast<const float2 *>(b_s + n);
+                                const float2 o = make_float2(v[i] + bb.x, v[i + 1] + bb.y);
+                                if constexpr (BF16) {
+                                    __nv_bfloat162 h2 = __float22bfloat162_rn(o);
+                                    *reinterpret_cast<__nv_bfloat162 *>(dst) = h2;
+                                } else {
+                                    *reinterpret_cast<float2 *>(dst) = o;
+                                }
+                            }
+                        }
+                    }
+                } else {
+                    for (int cb = 0; cb < NP / 16; ++cb) {
+                        float v[16];
+                        tmem_ld16(taddr + cb * 16, v);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int n = cb * 16 + i;
+                            if (n < HC) st_elem(out_l + row * HC + n, v[i] + b_s[n]);
+                            else if (n < 2 * HC) st_elem(out_r + row * HC + (n - HC), v[i] + b_s[n]);
+                        }
                     }
                 }
                 tc_fence_before();
@@ -283,7 +350,7 @@ bool project_tc_supported(int F, int HC) {
     return tc_fwd_smem<false>(F, HC, KPt, NP, 2).total <= 200 * 1024;
 }
 
-template <bool BF16>
+template <bool BF16, int FT, int HT>
 static int launch_fwd_tc(TcFwdArgs &a, cudaStream_t st) {
     a.KP = BF16 ? ((a.F + 15) / 16) * 16 : ((a.F + 7) / 8) * 8;
     a.NP = ((2 * a.HC + 15) / 16) * 16;
@@ -295,7 +362,7 @@ static int launch_fwd_tc(TcFwdArgs &a, cudaStream_t st) {
     while (a.stages > 2 && tc_fwd_smem<BF16>(a.F, a.HC, a.KP, a.NP, a.stages).total > 200u * 1024u) --a.stages;
     const TcFwdSmem L = tc_fwd_smem<BF16>(a.F, a.HC, a.KP, a.NP, a.stages);
     TG_REQUIRE(L.total <= 200u * 1024u, TECGAT_ENOSUP, "project_fwd(tc): F=%d, HC=%d needs %u B shared memory", a.F, a.HC, L.total);
-    auto kern = project_fwd_tc_kernel<BF16>;
+    auto kern = project_fwd_tc_kernel<BF16, FT, HT>;
     TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     const int64_t tiles = (a.R + kTileM - 1) / kTileM;
     const int grid = (int)(tiles < 2 * 148 ? tiles : 2 * 148);
@@ -312,7 +379,11 @@ int project_fwd_tc(const float *x, const float *wl, const float *bl, const float
     TcFwdArgs a;
     a.x = x; a.wl = wl; a.bl = bl; a.wr = wr; a.br = br; a.xl = xl; a.xr = xr;
     a.R = R; a.F = F; a.HC = HC;
-    return dtype == TECGAT_BF16 ? launch_fwd_tc<true>(a, st) : launch_fwd_tc<false>(a, st);
+    // straight-line specialisations for the reference's shapes (train.py:263-266 default, README variant); generic otherwise
+    if (F == 22 && HC == 22) return dtype == TECGAT_BF16 ? launch_fwd_tc<true, 22, 22>(a, st) : launch_fwd_tc<false, 22, 22>(a, st);
+    if (F == 10 && HC == 10) return dtype == TECGAT_BF16 ? launch_fwd_tc<true, 10, 10>(a, st) : launch_fwd_tc<false, 10, 10>(a, st);
+    if (F == 22 && HC == 44) return dtype == TECGAT_BF16 ? launch_fwd_tc<true, 22, 44>(a, st) : launch_fwd_tc<false, 22, 44>(a, st);
+    return dtype == TECGAT_BF16 ? launch_fwd_tc<true, 0, 0>(a, st) : launch_fwd_tc<false, 0, 0>(a, st);
 }
 
 // =====================================================================================================================
