@@ -151,7 +151,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "samples_per_s": batch * len(times) / total,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -324,11 +324,20 @@ def run_gpu_arm(args):
                 "sample": f"B=2 x {L_IN} snapshots x {N_NODES} nodes, fp32, oracle port of PyG GATv2Conv fwd+bwd, best of 3 "
                           f"({best * 1e3:.0f} ms)",
             }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier(device_ids=[local_rank])
         dist.destroy_process_group()
     return 0
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
@@ -342,6 +351,12 @@ def main():
     ap.add_argument("--autocast", action="store_true", help="bf16-autocast contract instead of fp32")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: native libraries (NCCL prints its version banner there) and stray prints
+    # are sent to stderr by pointing fd 1 at fd 2; emit() writes the line to the saved descriptor.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference_arm(args)
     return run_gpu_arm(args)

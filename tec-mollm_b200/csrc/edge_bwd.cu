@@ -39,11 +39,13 @@ struct EdgeBwdArgs {
     int32_t per_st, per_f, per_stat;  // 16-byte row periods (rows) of xl/xr, of g/y and of stat
     // shared-memory map (bytes): [barriers 128][tile table][y window][out staging][stage 0][stage 1]..
     // stage: [slab][stat window raw][delta|stat planes (H x cap_rows float2)][xl window][xr window][g window]
-    uint32_t stage_bytes, off_meta, off_stage0, off_y, off_out, off_statraw, off_ds, off_xl, off_xr, off_g;
+    uint32_t stage_bytes, off_meta, off_red, off_stage0, off_y, off_out, off_statraw, off_ds, off_xl, off_xr, off_g;
+    int32_t max_flushes;  // partial rows per CTA
     int64_t items;
 };
 
 constexpr int kBarConsumers = 1;  // named barrier id used by the consumer warps
+constexpr int kFlushItems = 256;   // items between two flushes of the per-lane fp32 parameter-gradient sums
 
 __device__ __forceinline__ void bar_sync_named(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
@@ -192,7 +194,8 @@ __device__ __forceinline__ void bwd_lane(const CV<C> &attp, const CV<C> &attm, c
     }
 }
 
-template <int C, typename ST, bool VEC>
+// HT > 0: compile-time number of heads (address arithmetic folds); 0: runtime
+template <int C, typename ST, bool VEC, int HT>
 __global__ void __launch_bounds__(256, 1) edge_bwd_kernel(const EdgeBwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem);
@@ -204,7 +207,7 @@ __global__ void __launch_bounds__(256, 1) edge_bwd_kernel(const EdgeBwdArgs a) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ncw = (blockDim.x >> 5) - 1;
     const int nct = ncw * 32;  // consumer threads
-    const int H = a.H, HC = H * C, T = a.T, N = a.N;
+    const int H = HT > 0 ? HT : a.H, HC = H * C, T = a.T, N = a.N;
     const int Ts = (T + 7) & ~7;  // row stride of the slab sections
     const int NS = a.num_stages;
     const uint32_t RB_ST = (uint32_t)HC * sizeof(ST), RB_F = (uint32_t)HC * 4u, RB_STAT = (uint32_t)H * 4u;
@@ -280,7 +283,7 @@ __global__ void __launch_bounds__(256, 1) edge_bwd_kernel(const EdgeBwdArgs a) {
     }
 
     // ================================ consumer warps ================================
-    const int npw = a.npw;
+    const int npw = HT > 0 ? 32 / pad_heads(HT) : a.npw;
     const int nw = lane & (npw - 1);
     const int h = lane / npw;
     const int node_l = warp * npw + nw;
@@ -296,10 +299,43 @@ __global__ void __launch_bounds__(256, 1) edge_bwd_kernel(const EdgeBwdArgs a) {
     const uint32_t head_key = dropout_head_key((uint32_t)hh);
     uint32_t key = 0;
     int key_snap = -1;
-    // persistent fp64 partial sums of d att and d bias for this lane's (head, channel arrangement)
-    double datt_p[CV<C>::NP > 0 ? CV<C>::NP : 1][2], datt_s = 0.0, dbias_p[CV<C>::NP > 0 ? CV<C>::NP : 1][2], dbias_s = 0.0;
+    // per-lane fp32 partial sums of d att and d bias: one term per item, flushed to a CTA partial row every kFlushItems
+    // items (the second stage sums all rows in fp64)
+    CV<C> acc_att, acc_bias;
+    cv_zero(acc_att);
+    cv_zero(acc_bias);
+    float *red = reinterpret_cast<float *>(smem + a.off_red);  // (ncw, H, 2, C) flush scratch
+    int since_flush = 0, flushes = 0;
+    auto flush = [&]() {
+        // fixed-order reduction: lanes of a head inside the warp (xor tree), then the warps; one partial row per flush
+        auto put = [&](int which, int c, float v) {
+            for (int off = npw >> 1; off > 0; off >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, off);
+            if (nw == 0 && head_ok) red[((warp * H + hh) * 2 + which) * C + c] = v;
+        };
 #pragma unroll
-    for (int i = 0; i < CV<C>::NP; ++i) datt_p[i][0] = datt_p[i][1] = dbias_p[i][0] = dbias_p[i][1] = 0.0;
+        for (int i = 0; i < CV<C>::NP; ++i) {
+            put(0, 2 * i + par, acc_att.p[i].x);
+            put(0, 2 * i + 1 + par, acc_att.p[i].y);
+            put(1, 2 * i + par, acc_bias.p[i].x);
+            put(1, 2 * i + 1 + par, acc_bias.p[i].y);
+        }
+        if (CV<C>::ODD) {
+            put(0, par ? 0 : C - 1, acc_att.s);
+            put(1, par ? 0 : C - 1, acc_bias.s);
+        }
+        bar_sync_named(kBarConsumers, nct);
+        if (ctid < 2 * HC) {
+            const int which = ctid / HC, j = ctid - which * HC, hd = j / C, c = j - hd * C;
+            double v = 0.0;
+            for (int wq = 0; wq < ncw; ++wq) v += (double)red[((wq * H + hd) * 2 + which) * C + c];
+            a.partials[((int64_t)blockIdx.x * a.max_flushes + flushes) * 2 * HC + which * HC + j] = (float)v;
+        }
+        bar_sync_named(kBarConsumers, nct);
+        cv_zero(acc_att);
+        cv_zero(acc_bias);
+        ++flushes;
+        since_flush = 0;
+    };
     ST *out_l = reinterpret_cast<ST *>(smem + a.off_out) + warp * npw * HC;               // d xl rows of this warp
     ST *out_r = reinterpret_cast<ST *>(smem + a.off_out) + (size_t)T * HC + warp * npw * HC;  // d xr rows
 
@@ -453,51 +489,26 @@ __global__ void __launch_bounds__(256, 1) edge_bwd_kernel(const EdgeBwdArgs a) {
                 cv_store<C, VEC>(static_cast<ST *>(a.dxr) + row * HC + hh * C, dxr, par);
             }
         }
-        // ---- parameter-gradient partials of this item (fp64 across items) ------------------------------------------
+        // ---- parameter-gradient partials of this item -------------------------------------------------------------------
         if (active) {
 #pragma unroll
             for (int i = 0; i < CV<C>::NP; ++i) {
-                datt_p[i][0] += (double)tatt.p[i].x;
-                datt_p[i][1] += (double)tatt.p[i].y;
-                dbias_p[i][0] += (double)g_v.p[i].x;
-                dbias_p[i][1] += (double)g_v.p[i].y;
+                acc_att.p[i] = __fadd2_rn(acc_att.p[i], tatt.p[i]);
+                acc_bias.p[i] = __fadd2_rn(acc_bias.p[i], g_v.p[i]);
             }
             if (CV<C>::ODD) {
-                datt_s += (double)tatt.s;
-                dbias_s += (double)g_v.s;
+                acc_att.s += tatt.s;
+                acc_bias.s += g_v.s;
             }
         }
+        if (++since_flush == kFlushItems) flush();
         if (++tile == a.num_tiles) { tile = 0; ++snap; }
     }
 
-    // ---- CTA partial of d att / d bias: fixed-order reduction over the lanes of a head, then over the warps -------------
-    bar_sync_named(kBarConsumers, nct);  // every consumer warp is done with the rings: reuse the y window as scratch
-    double *scratch = reinterpret_cast<double *>(smem + a.off_y);  // (ncw, H, 2, C) doubles
-    {
-        auto put = [&](int which, int c, double v) {
-            // sum over the npw lanes of this head inside the warp (xor-shuffle tree: fixed order)
-            for (int off = npw >> 1; off > 0; off >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, off);
-            if (nw == 0 && head_ok) scratch[((warp * H + hh) * 2 + which) * C + c] = v;
-        };
-#pragma unroll
-        for (int i = 0; i < CV<C>::NP; ++i) {
-            put(0, 2 * i + par, datt_p[i][0]);
-            put(0, 2 * i + 1 + par, datt_p[i][1]);
-            put(1, 2 * i + par, dbias_p[i][0]);
-            put(1, 2 * i + 1 + par, dbias_p[i][1]);
-        }
-        if (CV<C>::ODD) {
-            put(0, par ? 0 : C - 1, datt_s);
-            put(1, par ? 0 : C - 1, dbias_s);
-        }
-    }
-    bar_sync_named(kBarConsumers, nct);
-    if (ctid < 2 * HC) {
-        const int which = ctid / HC, j = ctid - which * HC, hd = j / C, c = j - hd * C;
-        double v = 0.0;
-        for (int wq = 0; wq < ncw; ++wq) v += scratch[((wq * H + hd) * 2 + which) * C + c];
-        a.partials[(int64_t)blockIdx.x * 2 * HC + which * HC + j] = (float)v;
-    }
+    flush();
+    // rows this CTA did not use (fewer items than the largest CTA): zeros
+    for (; flushes < a.max_flushes; ++flushes)
+        if (ctid < 2 * HC) a.partials[((int64_t)blockIdx.x * a.max_flushes + flushes) * 2 * HC + ctid] = 0.f;
 }
 
 struct StagePickBwd {
@@ -555,7 +566,20 @@ static StagePickBwd pick_stages_bwd(const tg_tiling &tl, const BwdGeom &g, size_
     return best;
 }
 
-template <int C, typename ST, bool VEC>
+static int bwd_grid(const tecgat_plan_t *plan, int32_t snapshots) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t items = int64_t(plan->bwd.num_tiles) * snapshots;
+    return (int)std::min<int64_t>(items, sms);
+}
+
+static int bwd_max_flushes(const tecgat_plan_t *plan, int32_t snapshots) {  // partial rows per CTA
+    const int64_t items = int64_t(plan->bwd.num_tiles) * snapshots;
+    const int g = bwd_grid(plan, snapshots);
+    return (int)(((items + g - 1) / g) / kFlushItems + 1);
+}
+
+template <int C, typename ST, bool VEC, int HT = 0>
 static int launch_bwd(EdgeBwdArgs a, const tecgat_plan_t *plan, int grid, cudaStream_t st) {
     const tg_tiling &tl = plan->bwd;
     const int H = a.H, HC = H * C, T = tl.T;
@@ -565,9 +589,9 @@ static int launch_bwd(EdgeBwdArgs a, const tecgat_plan_t *plan, int grid, cudaSt
     BwdGeom g{T, H, HC, sizeof(ST), row_period(uint32_t(HC * sizeof(ST))), row_period(uint32_t(HC * 4)), row_period(uint32_t(H * 4))};
     a.per_st = g.per_st; a.per_f = g.per_f; a.per_stat = g.per_stat;
     const size_t out_bytes = (2 * size_t(T) * HC * sizeof(ST) + 15) & ~size_t(15);
-    const size_t scratch_bytes = size_t(ncw) * H * 2 * C * sizeof(double);  // end-of-kernel reduction, aliases the y window
+    const size_t red_bytes = (size_t(ncw) * H * 2 * C * sizeof(float) + 15) & ~size_t(15);
     const size_t meta_bytes = tl.num_tiles <= kMetaSmemTiles ? size_t(tl.num_tiles) * 32 : 0;
-    const size_t fixed = 128 + meta_bytes + out_bytes;
+    const size_t fixed = 128 + meta_bytes + red_bytes + out_bytes;
     const char *env = getenv("TECGAT_BWD_STAGES");
     const int want = env ? std::max(1, std::min(kMaxStages, atoi(env))) : 2;
     const StagePickBwd sp = pick_stages_bwd(tl, g, fixed, want);
@@ -575,28 +599,21 @@ static int launch_bwd(EdgeBwdArgs a, const tecgat_plan_t *plan, int grid, cudaSt
     a.cap_rows = sp.cap_rows;
     a.cap_kin = sp.num_stages > 0 ? sp.cap_kin : -1;
     a.cap_kout = sp.cap_kout;
-    size_t ybytes = g.win_f(a.cap_rows);
-    if (ybytes < scratch_bytes) ybytes = (scratch_bytes + 15) & ~size_t(15);
+    const size_t ybytes = g.win_f(a.cap_rows);
     a.off_meta = 128;
-    a.off_y = (uint32_t)(128 + meta_bytes);
+    a.off_red = (uint32_t)(128 + meta_bytes);
+    a.off_y = (uint32_t)(a.off_red + red_bytes);
     a.off_out = (uint32_t)(a.off_y + ybytes);
     a.off_stage0 = (uint32_t)((a.off_out + out_bytes + 127) & ~size_t(127));
     a.stage_bytes = sp.stage_bytes;
     a.off_statraw = sp.off_statraw; a.off_ds = sp.off_ds; a.off_xl = sp.off_xl; a.off_xr = sp.off_xr; a.off_g = sp.off_g;
     const size_t smem = a.off_stage0 + size_t(sp.num_stages) * a.stage_bytes;
     TG_REQUIRE(smem <= 227 * 1024, TECGAT_ENOSUP, "edge_bwd: %zu B shared memory needed (tile %d x %d channels)", smem, T, HC);
-    auto kern = edge_bwd_kernel<C, ST, VEC>;
+    auto kern = edge_bwd_kernel<C, ST, VEC, HT>;
     TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)grid, (ncw + 1) * 32, smem, st>>>(a);
     TG_LAUNCH_CHECK();
     return TECGAT_OK;
-}
-
-static int bwd_grid(const tecgat_plan_t *plan, int32_t snapshots) {
-    int dev = 0, sms = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int64_t items = int64_t(plan->bwd.num_tiles) * snapshots;
-    return (int)std::min<int64_t>(items, sms);
 }
 
 }  // namespace tg
@@ -604,7 +621,7 @@ static int bwd_grid(const tecgat_plan_t *plan, int32_t snapshots) {
 extern "C" int64_t tecgat_edge_bwd_workspace(const tecgat_plan_t *plan, int32_t snapshots, int32_t heads,
                                              int32_t out_channels) {
     if (!plan || snapshots <= 0 || heads <= 0 || out_channels <= 0) return 0;
-    return int64_t(tg::bwd_grid(plan, snapshots)) * 2 * heads * out_channels * (int64_t)sizeof(float);
+    return int64_t(tg::bwd_grid(plan, snapshots)) * tg::bwd_max_flushes(plan, snapshots) * 2 * heads * out_channels * (int64_t)sizeof(float);
 }
 
 extern "C" int tecgat_edge_bwd(const tecgat_plan_t *plan, const void *xl, const void *xr, const float *att,
@@ -647,6 +664,7 @@ extern "C" int tecgat_edge_bwd(const tecgat_plan_t *plan, const void *xl, const 
     a.literal = (mode == TECGAT_MODE_LITERAL);
     a.items = int64_t(tl.num_tiles) * snapshots;
     const int grid = bwd_grid(plan, snapshots);
+    a.max_flushes = bwd_max_flushes(plan, snapshots);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int rc = TECGAT_ENOSUP;
 #define TG_CASE(CC)                                                                                                          \
@@ -654,6 +672,10 @@ extern "C" int tecgat_edge_bwd(const tecgat_plan_t *plan, const void *xl, const 
         if (vec) rc = dtype == TECGAT_F32 ? launch_bwd<CC, float, true>(a, plan, grid, st) : launch_bwd<CC, __nv_bfloat16, true>(a, plan, grid, st); \
         else if constexpr ((CC % 2) == 1) rc = dtype == TECGAT_F32 ? launch_bwd<CC, float, false>(a, plan, grid, st) : launch_bwd<CC, __nv_bfloat16, false>(a, plan, grid, st); \
         break;
+    if (heads == 2 && vec && (out_channels == 11 || out_channels == 5)) {  // compile-time heads for the reference's shapes
+        if (out_channels == 11) rc = dtype == TECGAT_F32 ? launch_bwd<11, float, true, 2>(a, plan, grid, st) : launch_bwd<11, __nv_bfloat16, true, 2>(a, plan, grid, st);
+        else rc = dtype == TECGAT_F32 ? launch_bwd<5, float, true, 2>(a, plan, grid, st) : launch_bwd<5, __nv_bfloat16, true, 2>(a, plan, grid, st);
+    } else
     switch (out_channels) {
         TG_FOR_EACH_C(TG_CASE)
         default:
@@ -663,5 +685,5 @@ extern "C" int tecgat_edge_bwd(const tecgat_plan_t *plan, const void *xl, const 
 #undef TG_CASE
     if (rc != TECGAT_OK) return rc;
     ReduceSegs segs = {{datt, dbias, nullptr, nullptr}, {0, HC, 0, 0}, {HC, 2 * HC, 0, 0}};
-    return reduce_columns(a.partials, grid, 2 * HC, segs, st);
+    return reduce_columns(a.partials, int64_t(grid) * a.max_flushes, 2 * HC, segs, st);
 }

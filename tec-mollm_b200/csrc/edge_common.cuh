@@ -154,7 +154,7 @@ __device__ __forceinline__ float fast_log2(float x) {
 }
 
 // ---- lane <-> (node, head) ----------------------------------------------------------------------------------------
-__host__ __device__ __forceinline__ int pad_heads(int H) {  // next power of two (<= 32)
+__host__ __device__ constexpr int pad_heads(int H) {  // next power of two (<= 32)
     int hp = 1;
     while (hp < H) hp <<= 1;
     return hp;

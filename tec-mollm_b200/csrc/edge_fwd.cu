@@ -119,7 +119,8 @@ __device__ __forceinline__ void fwd_lane(const EdgeFwdArgs &a, const CV<C> &attp
     stat = l > 0.f ? shift + fast_log2(l) : 0.f;
 }
 
-template <int C, typename ST, bool VEC>
+// HT > 0: compile-time number of heads (address arithmetic folds); 0: runtime
+template <int C, typename ST, bool VEC, int HT>
 __global__ void __launch_bounds__(512, 1) edge_fwd_kernel(const EdgeFwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem);
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(512, 1) edge_fwd_kernel(const EdgeFwdArgs a) {
     const tg_tile_meta *meta_s = reinterpret_cast<const tg_tile_meta *>(smem + a.off_meta);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ncw = (blockDim.x >> 5) - 1;  // consumer warps; the last warp is the producer
-    const int H = a.H, HC = H * C, T = a.T, N = a.N;
+    const int H = HT > 0 ? HT : a.H, HC = H * C, T = a.T, N = a.N;
     const int Ts = (T + 7) & ~7;  // row stride of the slab sections
     const int NS = a.num_stages;
     constexpr uint32_t ES = sizeof(ST);
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(512, 1) edge_fwd_kernel(const EdgeFwdArgs a) {
     }
 
     // ================================ consumer warps ================================
-    const int npw = a.npw;                 // nodes per warp = 32 / padded heads
+    const int npw = HT > 0 ? 32 / pad_heads(HT) : a.npw;                 // nodes per warp = 32 / padded heads
     const int nw = lane & (npw - 1);       // node within the warp (npw is a power of two)
     const int h = lane / npw;              // head (>= H: padding lane)
     const int node_l = warp * npw + nw;
@@ -308,7 +309,7 @@ static StagePick pick_stages(const tg_tiling &tl, int T, int HC, size_t es, int 
     return best;
 }
 
-template <int C, typename ST, bool VEC>
+template <int C, typename ST, bool VEC, int HT = 0>
 static int launch_fwd(EdgeFwdArgs a, const tecgat_plan_t *plan, cudaStream_t st) {
     const tg_tiling &tl = plan->fwd;
     const int HC = a.H * C, T = tl.T;
@@ -330,7 +331,7 @@ static int launch_fwd(EdgeFwdArgs a, const tecgat_plan_t *plan, cudaStream_t st)
     a.off_xr = sp.off_xr;
     a.off_xl = sp.off_xl;
     const size_t smem = a.off_stage0 + size_t(a.num_stages) * a.stage_bytes;
-    auto kern = edge_fwd_kernel<C, ST, VEC>;
+    auto kern = edge_fwd_kernel<C, ST, VEC, HT>;
     TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 0;
     TG_CUDA(cudaGetDevice(&dev));
@@ -384,6 +385,10 @@ extern "C" int tecgat_edge_fwd(const tecgat_plan_t *plan, const void *xl, const 
         if (vec) return dtype == TECGAT_F32 ? launch_fwd<CC, float, true>(a, plan, st) : launch_fwd<CC, __nv_bfloat16, true>(a, plan, st); \
         if constexpr ((CC % 2) == 1) return dtype == TECGAT_F32 ? launch_fwd<CC, float, false>(a, plan, st) : launch_fwd<CC, __nv_bfloat16, false>(a, plan, st); \
         break;
+    if (heads == 2 && vec) {  // the reference's shapes (train.py:263-266, README variant): compile-time heads
+        if (out_channels == 11) return dtype == TECGAT_F32 ? launch_fwd<11, float, true, 2>(a, plan, st) : launch_fwd<11, __nv_bfloat16, true, 2>(a, plan, st);
+        if (out_channels == 5) return dtype == TECGAT_F32 ? launch_fwd<5, float, true, 2>(a, plan, st) : launch_fwd<5, __nv_bfloat16, true, 2>(a, plan, st);
+    }
     switch (out_channels) {
         TG_FOR_EACH_C(TG_CASE)
         default:
