@@ -295,6 +295,7 @@ def run_gpu_arm(args):
             gbs = rows * bpr[k] / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
             phases[k] = {"ms": ms, "bytes_per_row": bpr[k], "achieved_gbs": gbs, "frac": gbs / peak}
         dom = max(phase_ms, key=phase_ms.get)
+        traffic, traffic_src = measured_traffic(dom, rows, args)
         step_ms = elapsed_ms / args.steps
         value = world * edges_per_step * args.steps / (elapsed_ms * 1e-3)
         e2e_value = world * edges_per_step * args.steps / (e2e_ms * 1e-3)
@@ -305,7 +306,7 @@ def run_gpu_arm(args):
             "samples_per_s": world * B * args.steps / (elapsed_ms * 1e-3),
             "roofline": {
                 "kernel": dom, "bound": "hbm", "achieved": phases[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": phases[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                "frac": phases[dom]["frac"], "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": rows * bpr[dom], "share_of_step": phase_ms[dom] / step_ms,
             },
             "phases": phases,
@@ -329,6 +330,22 @@ def run_gpu_arm(args):
         dist.barrier(device_ids=[local_rank])
         dist.destroy_process_group()
     return 0
+
+
+def measured_traffic(kernel, rows, args):
+    """DRAM bytes of one launch of `kernel` from the committed ncu --set full capture (profiles/traffic_r01.json): measured
+    per row at the default workload (fp32, B=128 x 48 snapshots); other sizes scale it by rows, other dtypes report null."""
+    path = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    if args.autocast or not os.path.exists(path):
+        return None, None
+    try:
+        with open(path) as f:
+            t = json.load(f)
+        per_row = t["kernels"][kernel]["dram_bytes_per_row"]
+    except (KeyError, ValueError):
+        return None, None
+    src = "ncu --set full, dram read+write per launch, " + ("this workload" if rows == t["rows"] else f"per-row figure measured at {t['rows']} rows")
+    return per_row * rows, src + " (profiles/r01_ncu_full_B128.csv)"
 
 
 _REAL_STDOUT = None

@@ -598,6 +598,7 @@ static int launch_bwd(EdgeBwdArgs a, const tecgat_plan_t *plan, int grid, cudaSt
     a.num_stages = sp.num_stages > 0 ? sp.num_stages : 1;
     a.cap_rows = sp.cap_rows;
     a.cap_kin = sp.num_stages > 0 ? sp.cap_kin : -1;
+    if (getenv("TECGAT_EDGE_NOSTAGE")) a.cap_kin = -1;  // tests: force the gather-from-global path
     a.cap_kout = sp.cap_kout;
     const size_t ybytes = g.win_f(a.cap_rows);
     a.off_meta = 128;

@@ -327,6 +327,7 @@ static int launch_fwd(EdgeFwdArgs a, const tecgat_plan_t *plan, cudaStream_t st)
     a.num_stages = sp.num_stages > 0 ? sp.num_stages : 1;
     a.cap_rows = sp.cap_rows;
     a.cap_k = sp.num_stages > 0 ? sp.cap_k : -1;  // -1: nothing is staged
+    if (getenv("TECGAT_EDGE_NOSTAGE")) a.cap_k = -1;  // tests: force the gather-from-global path
     a.stage_bytes = sp.stage_bytes;
     a.off_xr = sp.off_xr;
     a.off_xl = sp.off_xl;

@@ -216,6 +216,36 @@ def test_random_graphs_fp32(cuda_device, S, N, F, H, C, E):
     _check(y, grads, y_ref, g_ref, TOL_F32, f"S{S}N{N}F{F}H{H}C{C}")
 
 
+@pytest.mark.parametrize("S,N,F,H,C,E", [(2, 300, 22, 2, 11, 3000), (2, 90, 5, 4, 3, 500), (1, 3000, 22, 2, 11, 24000)])
+def test_gather_path_when_windows_are_not_staged(cuda_device, monkeypatch, S, N, F, H, C, E):
+    """Tiles whose row window does not fit a shared-memory stage gather neighbour rows from global memory.  The last
+    case gets there naturally (random graph: every tile's window spans all 3000 rows); the others force it."""
+    if N < 3000:
+        monkeypatch.setenv("TECGAT_EDGE_NOSTAGE", "1")
+    ei = random_graph(N, E, seed=N + E + 7, isolated=(5,))
+    x, gy, p = _rand_case(S, N, F, H, C, seed=S * 10 + N)
+    enc = _encoder(F, H, C, p, cuda_device).eval()
+    y, grads = _run_cuda(enc, x, ei, gy)
+    y_ref, g_ref, _ = oracle_with_kernel_branches(x, ei, p, H, C, gy, cuda_device)
+    _check(y, grads, y_ref, g_ref, TOL_F32, f"gather S{S}N{N}")
+
+
+def test_softmax_shift_retry_on_huge_score_spread(cuda_device):
+    """The kernels shift the softmax by the self-loop score; rows where another score exceeds it by more than ~2^100
+    are redone with the exact maximum.  att scaled by 400 makes score differences of several hundred."""
+    S, N, F, H, C, E = 2, 120, 22, 2, 11, 900
+    ei = random_graph(N, E, seed=99, isolated=(2,))
+    x, gy, p = _rand_case(S, N, F, H, C, seed=77)
+    p["att"] = p["att"] * 400.0
+    enc = _encoder(F, H, C, p, cuda_device).eval()
+    y, grads = _run_cuda(enc, x, ei, gy)
+    y_ref, g_ref, _ = oracle_with_kernel_branches(x, ei, p, H, C, gy, cuda_device)
+    assert torch.isfinite(y).all()
+    assert rel_err(y, y_ref) <= 2e-5      # alpha is a near one-hot: exp2 argument errors scale with |score| ~ 1e3
+    for k in ("x", "att", "lin_l.weight", "lin_r.weight"):
+        assert torch.isfinite(grads[k]).all() and rel_err(grads[k], g_ref[k]) <= 1e-3, k
+
+
 def test_empty_edge_list_and_single_node(cuda_device):
     """No edges at all: every node attends only to its self loop (y = W_l x + b_l + bias)."""
     S, N, F, H, C = 2, 9, 5, 2, 3
