@@ -234,13 +234,15 @@ __global__ void __launch_bounds__(kThreads, 1) project_bwd_rt_kernel(const Args 
             const ST *d = reinterpret_cast<const ST *>(st + d_off);
             const float *xp = reinterpret_cast<const float *>(st + L.off_x) + 12 * u;
             mbar_wait(&full[s], (it / kStages) & 1);
+            const ST *dp = d + slice * HC;   // pointer increments (integer adds on the ALU pipe) instead of r * HC (IMAD: FMA pipe)
+            const float *xq = xp + slice * F;
 #pragma unroll 1
-            for (int r = slice; r < nr; r += kSlices) {  // interleaved rows: the slices of a warp hit different banks
+            for (int r = slice; r < nr; r += kSlices, dp += kSlices * HC, xq += kSlices * F) {
                 float2 dv[4], xv[6];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) dv[i] = ld_pair(d + r * HC + 2 * i);
+                for (int i = 0; i < 4; ++i) dv[i] = ld_pair(dp + 2 * i);
 #pragma unroll
-                for (int k = 0; k < 6; ++k) xv[k] = ld_pair(xp + r * F + 2 * k);
+                for (int k = 0; k < 6; ++k) xv[k] = ld_pair(xq + 2 * k);
                 if (u) xv[5].y = 1.f;  // column 23: the constant 1 of the bias gradient
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {

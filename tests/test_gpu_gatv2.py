@@ -205,6 +205,9 @@ def test_golden_fixtures_fp32(cuda_device, name, mode):
     (4, 90, 5, 4, 3, 500),      # four heads
     (2, 64, 9, 2, 16, 400),
     (2, 33, 4, 3, 4, 150),      # heads not a power of two
+    (3, 50, 6, 1, 5, 300),      # H*C odd: rows are not pair aligned (scalar-load instantiation), 20-byte rows
+    (2, 45, 8, 3, 3, 250),      # H*C = 9, padded head lanes
+    (5, 70, 22, 2, 11, 0),      # no edges but several snapshots: odd row offsets of every window
 ])
 def test_random_graphs_fp32(cuda_device, S, N, F, H, C, E):
     ei = random_graph(N, E, seed=N + E, isolated=(3,))
