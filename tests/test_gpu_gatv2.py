@@ -412,3 +412,36 @@ def test_works_inside_grad_scaler_and_optimizer_step(cuda_device):
         scaler.update()
         losses.append(loss.item())
     assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+
+
+def test_cuda_graph_capture_and_replay(cuda_device):
+    """The whole forward + backward is capturable in a CUDA graph once the plan exists (no hidden syncs, no host
+    callbacks, workspaces from the capturing allocator), and replays reproduce the eager results bit for bit."""
+    ei = torch.from_numpy(load_golden("graph_small150.npz")["edge_index"]).to(cuda_device)
+    N = int(ei.max().item()) + 1
+    S, F, H, C = 6, 22, 2, 11
+    x, gy, p = _rand_case(S, N, F, H, C, seed=5, dtype=torch.float32)
+    enc = _encoder(F, H, C, p, cuda_device).eval()
+    xs = x.to(cuda_device).requires_grad_(True)
+    gs = gy.to(cuda_device)
+    side = torch.cuda.Stream(cuda_device)
+    side.wait_stream(torch.cuda.current_stream(cuda_device))
+    with torch.cuda.stream(side):          # warm-up on a side stream, as torch.cuda.graph requires: builds the plan,
+        for _ in range(3):                 # sets the kernel attributes, creates the AccumulateGrad nodes on this stream
+            xs.grad = None
+            enc.zero_grad(set_to_none=True)
+            enc(xs, ei).backward(gs)
+        ref = {"y": enc(xs, ei).detach().clone(), "x": xs.grad.clone(), **{k: q.grad.clone() for k, q in enc.named_parameters()}}
+    torch.cuda.current_stream(cuda_device).wait_stream(side)
+    xs.grad = None
+    enc.zero_grad(set_to_none=True)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        yg = enc(xs, ei)
+        yg.backward(gs)
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize(cuda_device)
+    assert torch.equal(yg, ref["y"]) and torch.equal(xs.grad, ref["x"])
+    for k, q in enc.named_parameters():
+        assert torch.equal(q.grad, ref[k]), k
