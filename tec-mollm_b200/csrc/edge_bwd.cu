@@ -74,7 +74,7 @@ struct DropCfg {
     uint32_t thr, key;
     float inv_keep;
     __device__ __forceinline__ float q(uint32_t slot) const {
-        if (!thr) return 1.f;
+        // no branch on "dropout off": threshold 0 keeps every edge and inv_keep is 1 (the loop bodies stay one basic block)
         return dropout_bits(key, slot) >= thr ? inv_keep : 0.f;
     }
 };

@@ -67,7 +67,8 @@ __device__ __forceinline__ void fwd_lane(const EdgeFwdArgs &a, const CV<C> &attp
         return k < deg ? __ldg(col + k) : 0;
     };
     auto keep = [&](float w, int k) -> float {
-        if (!a.drop_thr) return w;
+        // no branch on "dropout off": threshold 0 keeps every edge and inv_keep is 1, so the loop body stays ONE basic
+        // block and the two edges of an iteration interleave freely
         return dropout_bits(key, slot0 + (uint32_t)k) >= a.drop_thr ? w * a.inv_keep : 0.f;
     };
 #pragma unroll 1
