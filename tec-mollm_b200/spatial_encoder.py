@@ -2,7 +2,8 @@
 
 Same constructor ``(in_channels, out_channels, heads=2, dropout=0.1)``, same attributes (``.gat_conv`` owning
 the PyG-named parameters, ``.output_channels``), same ``forward(x, edge_index, edge_weight=None)`` taking
-``x`` of shape ``(B*L, N, C_in)`` and returning ``(B*L, N, heads*out_channels)``.
+``x`` of shape ``(B*L, N, C_in)`` and returning ``(B*L, N, heads*out_channels)`` (extra leading dimensions, e.g. the
+``(B, L, N, C_in)`` tensor the reference permutes from, are accepted and kept).
 
 One extra keyword, ``snapshot_mode``: ``"shared"`` (default) applies the one-graph ``edge_index`` to every one of the
 ``B*L`` snapshots -- the semantics the reference intends (tec_mollm.py:86-88) and BASELINE.json measures;
@@ -35,9 +36,17 @@ class SpatialEncoder(nn.Module):
 
     def forward(self, x: torch.Tensor, edge_index: torch.Tensor, edge_weight: torch.Tensor = None) -> torch.Tensor:
         # edge_weight is accepted and ignored, exactly like the reference (modules.py:347,355)
-        if x.dim() != 3:
-            raise ValueError(f"x must be (B*L, N, C_in); got {tuple(x.shape)}")
-        snapshots, num_nodes, in_channels = x.shape
+        if x.dim() < 3:
+            raise ValueError(f"x must be (B*L, N, C_in) or (..., N, C_in); got {tuple(x.shape)}")
+        # Snapshots are independent given the shared graph, so ANY leading layout works: the reference's (L*B, N, C)
+        # (tec_mollm.py:84) or the (B, L, N, C) tensor it is permuted from -- passing that one directly saves the caller's
+        # permute copy; the output keeps the leading dimensions.
+        lead, (num_nodes, in_channels) = x.shape[:-2], x.shape[-2:]
+        snapshots = 1
+        for d in lead:
+            snapshots *= int(d)
+        if len(lead) > 1 and self.snapshot_mode == "literal":
+            raise ValueError("snapshot_mode='literal' reproduces the reference's flattened call: pass (B*L, N, C_in)")
         x2d = x.reshape(-1, in_channels)
         y = self.gat_conv.forward_snapshots(x2d, edge_index, snapshots, num_nodes, self.snapshot_mode)
-        return y.view(snapshots, num_nodes, self.output_channels)
+        return y.view(*lead, num_nodes, self.output_channels)

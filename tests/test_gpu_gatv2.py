@@ -445,3 +445,18 @@ def test_cuda_graph_capture_and_replay(cuda_device):
     assert torch.equal(yg, ref["y"]) and torch.equal(xs.grad, ref["x"])
     for k, q in enc.named_parameters():
         assert torch.equal(q.grad, ref[k]), k
+
+
+def test_four_dimensional_input_keeps_leading_dims(cuda_device):
+    """(B, L, N, C) straight from the embedding (no permute copy): same numbers as the reference's (L*B, N, C) call,
+    snapshot for snapshot."""
+    ei = torch.from_numpy(load_golden("graph_small150.npz")["edge_index"]).to(cuda_device)
+    N = int(ei.max().item()) + 1
+    B, L, F, H, C = 2, 3, 22, 2, 11
+    x, gy, p = _rand_case(B * L, N, F, H, C, seed=9, dtype=torch.float32)
+    enc = _encoder(F, H, C, p, cuda_device).eval()
+    x4 = x.view(B, L, N, F).to(cuda_device)
+    y4 = enc(x4, ei)
+    assert y4.shape == (B, L, N, H * C)
+    y3 = enc(x4.permute(1, 0, 2, 3).reshape(L * B, N, F), ei)          # tec_mollm.py:84
+    assert torch.equal(y3.view(L, B, N, H * C).permute(1, 0, 2, 3), y4)
