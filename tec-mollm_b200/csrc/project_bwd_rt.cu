@@ -27,12 +27,17 @@ namespace tg {
 namespace rt {
 constexpr int kRows = 128;   // rows per tile
 constexpr int kFP = 24;      // padded input channels (F <= 22: column 23 carries the constant 1)
-constexpr int kHP = 24;      // padded gradient columns per array (HC <= 24)
-constexpr int kTeams = 3, kTeamWarps = 5, kStages = 5;
+constexpr int kTeams = 3, kTeamWarps = 5;
 constexpr int kConsumers = kTeams * kTeamWarps * 32;
 constexpr int kThreads = kConsumers + 32;
-constexpr int kSlices = 8;   // 16-row slices of a tile (dW warps)
 constexpr int kPad = 128;    // zeroed bytes after every staged tile (threads read up to 2 elements past a row)
+// HP = padded gradient columns per array: 24 (HC <= 24: 8 row slices, 5 ring stages) or 48 (HC <= 48: 4 slices, 3 stages);
+// either way the 3 dW warps of a team are 96 threads = slices x (2 HP / 8 column tiles) x 2 input tiles
+template <int HP> struct Cfg {
+    static constexpr int kSlices = 192 / HP;
+    static constexpr int kStages = HP == 24 ? 5 : 3;
+    static constexpr int kOT = 2 * HP / 8;  // 8-column tiles over [dxl | dxr]
+};
 
 struct Args {
     const void *dxl, *dxr;
@@ -46,8 +51,9 @@ struct Args {
 struct Smem {
     uint32_t bars, w, stage0, stage_bytes, off_dr, off_x, dxst, dxst_bytes, total;
 };
-template <typename ST>
+template <typename ST, int HP>
 __host__ __device__ inline Smem layout(int F, int HC) {
+    constexpr int kStages = Cfg<HP>::kStages, kHP = HP;
     Smem s;
     uint32_t o = 0;
     s.bars = o; o += 128;
@@ -72,11 +78,12 @@ __device__ __forceinline__ float2 ld_pair(const __nv_bfloat16 *p) {
 }
 __device__ __forceinline__ void named_bar(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
-template <typename ST>
+template <typename ST, int HP>
 __global__ void __launch_bounds__(kThreads, 1) project_bwd_rt_kernel(const Args a) {
     extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int kHP = HP, kSlices = Cfg<HP>::kSlices, kStages = Cfg<HP>::kStages, kOT = Cfg<HP>::kOT;
     const int F = a.F, HC = a.HC;
-    const Smem L = layout<ST>(F, HC);
+    const Smem L = layout<ST, HP>(F, HC);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + L.bars), *empty = full + kStages;
     float *W_s = reinterpret_cast<float *>(smem + L.w);  // [2][kHP][kFP], zero padded
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -219,13 +226,13 @@ __global__ void __launch_bounds__(kThreads, 1) project_bwd_rt_kernel(const Args 
     } else {
         // -------- dW warps: thread = (16-row slice, gradient columns 8 ot .. 8 ot+7, input columns 12 u .. 12 u+11) -------------
         const int q = (tw - 2) * 32 + lane;  // 0 .. 95
-        const int slice = q / 12, ot = (q % 12) >> 1, u = q & 1;
+        const int slice = q / (2 * kOT), ot = (q % (2 * kOT)) >> 1, u = q & 1;
         float2 acc[8][6];
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll
             for (int k = 0; k < 6; ++k) acc[i][k] = make_float2(0.f, 0.f);
-        const uint32_t d_off = (ot < 3 ? 0u : L.off_dr) + (uint32_t)(8 * (ot < 3 ? ot : ot - 3)) * (uint32_t)sizeof(ST);
+        const uint32_t d_off = (ot < kOT / 2 ? 0u : L.off_dr) + (uint32_t)(8 * (ot < kOT / 2 ? ot : ot - kOT / 2)) * (uint32_t)sizeof(ST);
         for (int it = team; it < n_local; it += kTeams) {
             const int s = it % kStages;
             const int64_t r0 = (blockIdx.x + (int64_t)it * gridDim.x) * kRows;
@@ -296,7 +303,7 @@ static int grid_for(int64_t R) {
 bool project_bwd_rt_supported(int F, int HC, const void *dxl, const void *dxr, const void *x, const void *dx) {
     const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dxl) | reinterpret_cast<uintptr_t>(dxr) |
                            reinterpret_cast<uintptr_t>(dx)) & 15) == 0;
-    return aligned && F >= 2 && F <= rt::kFP - 2 && (F % 2) == 0 && HC >= 2 && HC <= rt::kHP && (HC % 2) == 0;
+    return aligned && F >= 2 && F <= rt::kFP - 2 && (F % 2) == 0 && HC >= 2 && HC <= 48 && (HC % 2) == 0;
 }
 
 int64_t project_bwd_rt_workspace(int64_t R, int F, int HC) { return int64_t(rt::grid_for(R)) * (2 * HC * F + 2 * HC) * (int64_t)sizeof(float); }
@@ -307,16 +314,18 @@ int project_bwd_rt(const void *dxl, const void *dxr, const float *x, const float
     a.dxl = dxl; a.dxr = dxr; a.x = x; a.wl = wl; a.wr = wr; a.dx = dx; a.partials = static_cast<float *>(workspace);
     a.R = R; a.F = F; a.HC = HC;
     const int grid = rt::grid_for(R);
-    if (dtype == TECGAT_F32) {
-        const rt::Smem L = rt::layout<float>(F, HC);
-        auto k = rt::project_bwd_rt_kernel<float>;
-        TG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-        k<<<grid, rt::kThreads, L.total, st>>>(a);
+    auto launch = [&](auto kern, const rt::Smem &L) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+        if (e != cudaSuccess) return e;
+        kern<<<grid, rt::kThreads, L.total, st>>>(a);
+        return cudaSuccess;
+    };
+    if (HC <= 24) {
+        if (dtype == TECGAT_F32) TG_CUDA(launch(rt::project_bwd_rt_kernel<float, 24>, rt::layout<float, 24>(F, HC)));
+        else TG_CUDA(launch(rt::project_bwd_rt_kernel<__nv_bfloat16, 24>, rt::layout<__nv_bfloat16, 24>(F, HC)));
     } else {
-        const rt::Smem L = rt::layout<__nv_bfloat16>(F, HC);
-        auto k = rt::project_bwd_rt_kernel<__nv_bfloat16>;
-        TG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-        k<<<grid, rt::kThreads, L.total, st>>>(a);
+        if (dtype == TECGAT_F32) TG_CUDA(launch(rt::project_bwd_rt_kernel<float, 48>, rt::layout<float, 48>(F, HC)));
+        else TG_CUDA(launch(rt::project_bwd_rt_kernel<__nv_bfloat16, 48>, rt::layout<__nv_bfloat16, 48>(F, HC)));
     }
     TG_LAUNCH_CHECK();
     const int O = 2 * HC;

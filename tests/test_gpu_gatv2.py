@@ -135,7 +135,7 @@ def test_projection_forward(cuda_device, impl, R, F, HC):
 
 
 @pytest.mark.parametrize("impl", ["ffma", "tc"])
-@pytest.mark.parametrize("R,F,HC,need_dx", [(1000, 22, 22, True), (128 * 700 + 13, 22, 22, True), (77, 10, 10, True),
+@pytest.mark.parametrize("R,F,HC,need_dx", [(1000, 22, 22, True), (128 * 700 + 13, 22, 22, True), (77, 10, 10, True), (128 * 40 + 5, 22, 44, True),
                                             (128 * 40, 22, 22, False), (300, 7, 6, True), (128 * 3 + 1, 22, 44, True)])
 def test_projection_backward(cuda_device, impl, R, F, HC, need_dx):
     """dx = dxl Wl + dxr Wr, dW = d^T x, db = sum d: tensor-core (3xTF32, TMEM-accumulated dW) and CUDA-core kernels vs
