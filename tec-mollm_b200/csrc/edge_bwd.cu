@@ -434,9 +434,19 @@ __global__ void __launch_bounds__(256, 1) edge_bwd_kernel(const EdgeBwdArgs a) {
             if (VEC) {  // rows are pair aligned (8 B fp32 / 4 B bf16) in shared and in global memory
                 using W = typename std::conditional<sizeof(ST) == 4, uint2, uint32_t>::type;
                 const W *sl = reinterpret_cast<const W *>(out_l), *sr = reinterpret_cast<const W *>(out_r);
-                for (int i = lane; i < nv * HC / 2; i += 32) {
-                    reinterpret_cast<W *>(dl_g)[i] = sl[i];
-                    reinterpret_cast<W *>(dr_g)[i] = sr[i];
+                if (HT > 0 && nv == npw) {  // full warp slice, compile-time trip count: straight-line copy
+                    constexpr int kWords = HT > 0 ? (32 / pad_heads(HT > 0 ? HT : 1)) * (HT > 0 ? HT : 1) * C / 2 : 0;
+#pragma unroll
+                    for (int i = 0; i < (kWords + 31) / 32; ++i)
+                        if (i * 32 + lane < kWords) {
+                            reinterpret_cast<W *>(dl_g)[i * 32 + lane] = sl[i * 32 + lane];
+                            reinterpret_cast<W *>(dr_g)[i * 32 + lane] = sr[i * 32 + lane];
+                        }
+                } else {
+                    for (int i = lane; i < nv * HC / 2; i += 32) {
+                        reinterpret_cast<W *>(dl_g)[i] = sl[i];
+                        reinterpret_cast<W *>(dr_g)[i] = sr[i];
+                    }
                 }
             } else {
                 for (int i = lane; i < nv * HC; i += 32) {

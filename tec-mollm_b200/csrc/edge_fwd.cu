@@ -238,7 +238,14 @@ __global__ void __launch_bounds__(512, 1) edge_fwd_kernel(const EdgeFwdArgs a) {
             if (VEC) {
                 const float2 *src = reinterpret_cast<const float2 *>(ybuf);
                 float2 *dst = reinterpret_cast<float2 *>(y_g);
-                for (int i = lane; i < nv * HC / 2; i += 32) dst[i] = src[i];
+                if (HT > 0 && nv == npw) {  // full warp slice, compile-time trip count: straight-line copy
+                    constexpr int kWords = HT > 0 ? (32 / pad_heads(HT > 0 ? HT : 1)) * (HT > 0 ? HT : 1) * C / 2 : 0;
+#pragma unroll
+                    for (int i = 0; i < (kWords + 31) / 32; ++i)
+                        if (i * 32 + lane < kWords) dst[i * 32 + lane] = src[i * 32 + lane];
+                } else {
+                    for (int i = lane; i < nv * HC / 2; i += 32) dst[i] = src[i];
+                }
             } else {
                 for (int i = lane; i < nv * HC; i += 32) y_g[i] = ybuf[i];
             }
