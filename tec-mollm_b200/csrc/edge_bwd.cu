@@ -36,6 +36,7 @@ struct EdgeBwdArgs {
     uint64_t seed;
     int32_t literal;
     int32_t cap_rows, cap_kin, cap_kout, num_stages;
+    int32_t semi;  // 1: rows too wide for shared memory -- stage only slab + stat + delta planes, gather the rows from L2
     int32_t per_st, per_f, per_stat;  // 16-byte row periods (rows) of xl/xr, of g/y and of stat
     // shared-memory map (bytes): [barriers 128][tile table][y window][out staging][stage 0][stage 1]..
     // stage: [slab][stat window raw][delta|stat planes (H x cap_rows float2)][xl window][xr window][g window]
@@ -194,8 +195,9 @@ __device__ __forceinline__ void bwd_lane(const CV<C> &attp, const CV<C> &attm, c
     }
 }
 
-// HT > 0: compile-time number of heads (address arithmetic folds); 0: runtime
-template <int C, typename ST, bool VEC, int HT>
+// HT > 0: compile-time number of heads (address arithmetic folds); 0: runtime.  SEMI: the semi-staged variant (rows too
+// wide for shared memory) is a separate instantiation so that the fully staged kernel's code stays compact.
+template <int C, typename ST, bool VEC, int HT, bool SEMI>
 __global__ void __launch_bounds__(256, 1) edge_bwd_kernel(const EdgeBwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem);
@@ -242,10 +244,23 @@ __global__ void __launch_bounds__(256, 1) edge_bwd_kernel(const EdgeBwdArgs a) {
             if (staged) {
                 const int64_t row0 = (int64_t)snap * N + lo;
                 unsigned char *stage = smem + a.off_stage0 + (size_t)ring.st * a.stage_bytes;
+                const WinCopy c3 = win_copy(a.stat, row0, win, RB_STAT, a.per_stat, Rtot);
+                if (SEMI) {  // slab + stat window only; the consumers gather xl / xr / g / y rows from global memory (L2)
+                    if (lane == 0) mbar_wait(&empty[ring.st], ring.ph ^ 1u);
+                    __syncwarp();
+                    if (c3.tail) {
+                        win_copy_tail(c3, stage + a.off_statraw, lane);
+                        __syncwarp();
+                    }
+                    if (lane == 0) {
+                        mbar_arrive_expect_tx(&full[ring.st], (uint32_t)m.slab_bytes + c3.mid);
+                        bulk_g2s(stage, a.slabs + m.slab_off, (uint32_t)m.slab_bytes, &full[ring.st]);
+                        if (c3.mid) bulk_g2s(stage + a.off_statraw, c3.src, c3.mid, &full[ring.st]);
+                    }
+                } else {
                 const WinCopy c0 = win_copy(a.xl, row0, win, RB_ST, a.per_st, Rtot);
                 const WinCopy c1 = win_copy(a.xr, row0, win, RB_ST, a.per_st, Rtot);
                 const WinCopy c2 = win_copy(a.gy, row0, win, RB_F, a.per_f, Rtot);
-                const WinCopy c3 = win_copy(a.stat, row0, win, RB_STAT, a.per_stat, Rtot);
                 const WinCopy c4 = win_copy(a.y, row0, win, RB_F, a.per_f, Rtot);
                 if (lane == 0) mbar_wait(&empty[ring.st], ring.ph ^ 1u);
                 __syncwarp();
@@ -274,8 +289,9 @@ __global__ void __launch_bounds__(256, 1) edge_bwd_kernel(const EdgeBwdArgs a) {
                     mbar_arrive_expect_tx(yfull, c4.mid);
                     if (c4.mid) bulk_g2s(smem + a.off_y, c4.src, c4.mid, yfull);
                 }
+                }
                 ring.advance(NS);
-                yph ^= 1u;
+                if (!SEMI) yph ^= 1u;
             }
             if (++tile == a.num_tiles) { tile = 0; ++snap; }
         }
@@ -366,59 +382,68 @@ __global__ void __launch_bounds__(256, 1) edge_bwd_kernel(const EdgeBwdArgs a) {
             const uint16_t *ell_in = reinterpret_cast<const uint16_t *>(degs + Ts) + node_l;
             const uint16_t *ell_out = ell_in + (size_t)kin_t * Ts;
             const uint16_t *slot_rel = ell_out + (size_t)kout_t * Ts;
-            const ST *xl_s = reinterpret_cast<const ST *>(stage + a.off_xl + win_skip(row0, RB_ST, a.per_st));
-            const ST *xr_s = reinterpret_cast<const ST *>(stage + a.off_xr + win_skip(row0, RB_ST, a.per_st));
-            const float *g_s = reinterpret_cast<const float *>(stage + a.off_g + win_skip(row0, RB_F, a.per_f));
             const float *stat_s = reinterpret_cast<const float *>(stage + a.off_statraw + win_skip(row0, RB_STAT, a.per_stat));
-            const float *y_s = reinterpret_cast<const float *>(smem + a.off_y + win_skip(row0, RB_F, a.per_f));
             float2 *ds = reinterpret_cast<float2 *>(stage + a.off_ds);  // [head][window row] -> (delta, stat)
             mbar_wait(&full[ring.st], ring.ph);
-            mbar_wait(yfull, yph);
-            // ---- pre-pass: delta = g . (y - bias).  Each lane takes the window rows node_l, node_l + T, .. of its head
-            //      (needed by the SOURCE role of every lane) and its own row (DESTINATION role: no waiting on other warps)
-            auto delta_of = [&](int r) -> float2 {
-                CV<C> gg, yy;
-                cv_load<C, VEC>(gg, g_s + r * HC + hh * C, par);
-                cv_load<C, VEC>(yy, y_s + r * HC + hh * C, par);
-                float2 d2 = make_float2(0.f, 0.f);
+            // The row windows are in shared memory (full staging) or stay in global memory (semi staging, rows too wide):
+            // the same code is inlined once per address space.
+            auto item_body = [&](auto semi_tag, const ST *xl_s, const ST *xr_s, const float *g_s, const float *y_s) {
+                constexpr bool kSemi = decltype(semi_tag)::value;
+                // ---- pre-pass: delta = g . (y - bias).  Each lane takes the window rows node_l, node_l + T, .. of its head
+                //      (needed by the SOURCE role of every lane) and its own row (DESTINATION role: no waiting on other warps)
+                auto delta_of = [&](int r) -> float2 {
+                    CV<C> gg, yy;
+                    cv_load<C, VEC>(gg, g_s + (ptrdiff_t)r * HC + hh * C, par);
+                    cv_load<C, VEC>(yy, y_s + (ptrdiff_t)r * HC + hh * C, par);
+                    float2 d2 = make_float2(0.f, 0.f);
 #pragma unroll
-                for (int q = 0; q < CV<C>::NP; ++q) d2 = __ffma2_rn(gg.p[q], __fadd2_rn(yy.p[q], make_float2(-bias_h.p[q].x, -bias_h.p[q].y)), d2);
-                float dl = d2.x + d2.y;
-                if (CV<C>::ODD) dl = fmaf(gg.s, yy.s - bias_h.s, dl);
-                return make_float2(dl, stat_s[r * H + hh]);
+                    for (int q = 0; q < CV<C>::NP; ++q) d2 = __ffma2_rn(gg.p[q], __fadd2_rn(yy.p[q], make_float2(-bias_h.p[q].x, -bias_h.p[q].y)), d2);
+                    float dl = d2.x + d2.y;
+                    if (CV<C>::ODD) dl = fmaf(gg.s, yy.s - bias_h.s, dl);
+                    return make_float2(dl, stat_s[r * H + hh]);
+                };
+                const int vl = n0 + node_l - lo;  // own row inside the window
+                const float2 dv = active ? delta_of(vl) : make_float2(0.f, 0.f);
+                if (head_ok)
+                    for (int r = node_l; r < win; r += T) ds[hh * a.cap_rows + r] = delta_of(r);
+                __syncwarp();
+                if (lane == 0) {
+                    if (!kSemi) mbar_arrive(yempty);  // y window may be refilled for the next item
+                    mbar_arrive(&dready[ring.st]);
+                }
+                int deg_in = 0, deg_out = 0;
+                uint32_t slot0 = 0;
+                if (active) {
+                    const int d = degs[node_l];
+                    deg_in = d & 0xFFFF;
+                    deg_out = d >> 16;
+                    if (lit) { deg_in = min(deg_in, 1); deg_out = min(deg_out, 1); }
+                    slot0 = (uint32_t)k0s[node_l];
+                }
+                const uint32_t slot_base = (uint32_t)hdr[3];
+                const float2 *ds_h = ds + hh * a.cap_rows;
+                uint64_t *dr_bar = &dready[ring.st];
+                const uint32_t dr_ph = ring.ph;
+                const int kmax_in = __reduce_max_sync(0xFFFFFFFFu, deg_in), kmax_out = __reduce_max_sync(0xFFFFFFFFu, deg_out);
+                bwd_lane<C, ST, VEC>(
+                    attp, attm, att_h, a.slope, drop, xl_s + hh * C, xr_s + hh * C, g_s + hh * C, HC, par, (ptrdiff_t)vl, dv, deg_in, kmax_in,
+                    deg_out, kmax_out, slot0, [&](int k) -> ptrdiff_t { return (ptrdiff_t)ell_in[k * Ts]; },
+                    [&](int k) -> ptrdiff_t { return (ptrdiff_t)ell_out[k * Ts]; },
+                    [&](int k) -> uint32_t { return slot_base + (uint32_t)slot_rel[k * Ts]; },
+                    [&](ptrdiff_t u, const CV<C> &) -> float2 { return ds_h[u]; }, [&]() { mbar_wait(dr_bar, dr_ph); }, active, dxl, dxr,
+                    tatt, g_v);
             };
-            const int vl = n0 + node_l - lo;  // own row inside the window
-            const float2 dv = active ? delta_of(vl) : make_float2(0.f, 0.f);
-            if (head_ok)
-                for (int r = node_l; r < win; r += T) ds[hh * a.cap_rows + r] = delta_of(r);
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(yempty);  // y window may be refilled for the next item
-                mbar_arrive(&dready[ring.st]);
+            if constexpr (SEMI) {
+                item_body(std::true_type{}, static_cast<const ST *>(a.xl) + row0 * HC, static_cast<const ST *>(a.xr) + row0 * HC,
+                          a.gy + row0 * HC, a.y + row0 * HC);
+            } else {
+                mbar_wait(yfull, yph);
+                yph ^= 1u;
+                item_body(std::false_type{}, reinterpret_cast<const ST *>(stage + a.off_xl + win_skip(row0, RB_ST, a.per_st)),
+                          reinterpret_cast<const ST *>(stage + a.off_xr + win_skip(row0, RB_ST, a.per_st)),
+                          reinterpret_cast<const float *>(stage + a.off_g + win_skip(row0, RB_F, a.per_f)),
+                          reinterpret_cast<const float *>(smem + a.off_y + win_skip(row0, RB_F, a.per_f)));
             }
-            yph ^= 1u;
-
-            int deg_in = 0, deg_out = 0;
-            uint32_t slot0 = 0;
-            if (active) {
-                const int d = degs[node_l];
-                deg_in = d & 0xFFFF;
-                deg_out = d >> 16;
-                if (lit) { deg_in = min(deg_in, 1); deg_out = min(deg_out, 1); }
-                slot0 = (uint32_t)k0s[node_l];
-            }
-            const uint32_t slot_base = (uint32_t)hdr[3];
-            const float2 *ds_h = ds + hh * a.cap_rows;
-            uint64_t *dr_bar = &dready[ring.st];
-            const uint32_t dr_ph = ring.ph;
-            const int kmax_in = __reduce_max_sync(0xFFFFFFFFu, deg_in), kmax_out = __reduce_max_sync(0xFFFFFFFFu, deg_out);
-            bwd_lane<C, ST, VEC>(
-                attp, attm, att_h, a.slope, drop, xl_s + hh * C, xr_s + hh * C, g_s + hh * C, HC, par, (ptrdiff_t)vl, dv, deg_in, kmax_in,
-                deg_out, kmax_out, slot0, [&](int k) -> ptrdiff_t { return (ptrdiff_t)ell_in[k * Ts]; },
-                [&](int k) -> ptrdiff_t { return (ptrdiff_t)ell_out[k * Ts]; },
-                [&](int k) -> uint32_t { return slot_base + (uint32_t)slot_rel[k * Ts]; },
-                [&](ptrdiff_t u, const CV<C> &) -> float2 { return ds_h[u]; }, [&]() { mbar_wait(dr_bar, dr_ph); }, active, dxl, dxr, tatt,
-                g_v);
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[ring.st]);
             ring.advance(NS);
@@ -535,8 +560,9 @@ struct BwdGeom {  // everything the stage sizes depend on
     size_t win_stat(int rows) const { return round16(uint32_t((rows + 2 * (per_stat - 1)) * H * 4)); }
     size_t ds(int rows) const { return round16(uint32_t(rows * H * 8)); }
     size_t stage(int rows, int kin, int kout) const { return slab(kin, kout) + win_stat(rows) + ds(rows) + 2 * win_st(rows) + win_f(rows); }
+    size_t stage_semi(int rows, int kin, int kout) const { return slab(kin, kout) + win_stat(rows) + ds(rows); }
 };
-static StagePickBwd pick_stages_bwd(const tg_tiling &tl, const BwdGeom &g, size_t fixed_bytes, int want_stages) {
+static StagePickBwd pick_stages_bwd(const tg_tiling &tl, const BwdGeom &g, size_t fixed_bytes, int want_stages, bool semi = false) {
     StagePickBwd best{0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     double best_score = -1.0;
     for (int ns = want_stages; ns >= 1; --ns) {
@@ -544,13 +570,16 @@ static StagePickBwd pick_stages_bwd(const tg_tiling &tl, const BwdGeom &g, size_
         std::vector<std::pair<size_t, int>> need;
         for (int t = 0; t < tl.num_tiles; ++t) {
             const tg_tile_meta &m = tl.h_meta[t];
-            if (m.eligible) need.push_back({g.stage(m.hi - m.lo, m.kin_kout & 0xFFFF, m.kin_kout >> 16), t});
+            if (m.eligible)
+                need.push_back({semi ? g.stage_semi(m.hi - m.lo, m.kin_kout & 0xFFFF, m.kin_kout >> 16)
+                                     : g.stage(m.hi - m.lo, m.kin_kout & 0xFFFF, m.kin_kout >> 16), t});
         }
         std::sort(need.begin(), need.end());
         for (auto &nt : need) {
             const tg_tile_meta &m = tl.h_meta[nt.second];
             const int r = std::max(cap_rows, std::max(m.hi - m.lo, g.T)), ki = std::max(kin, m.kin_kout & 0xFFFF), ko = std::max(kout, m.kin_kout >> 16);
-            const size_t total = fixed_bytes + g.win_f(r) /* the single y window */ + ns * g.stage(r, ki, ko) + 256;
+            const size_t total = semi ? fixed_bytes + ns * g.stage_semi(r, ki, ko) + 256
+                                      : fixed_bytes + g.win_f(r) /* the single y window */ + ns * g.stage(r, ki, ko) + 256;
             if (total > size_t(kEdgeSmemBudget)) break;
             cap_rows = r; kin = ki; kout = ko;
             ++staged;
@@ -569,7 +598,7 @@ static StagePickBwd pick_stages_bwd(const tg_tiling &tl, const BwdGeom &g, size_
             best.off_xl = best.off_ds + (uint32_t)g.ds(cap_rows);
             best.off_xr = best.off_xl + (uint32_t)g.win_st(cap_rows);
             best.off_g = best.off_xr + (uint32_t)g.win_st(cap_rows);
-            best.stage_bytes = (uint32_t)g.stage(cap_rows, kin, kout);
+            best.stage_bytes = (uint32_t)(semi ? g.stage_semi(cap_rows, kin, kout) : g.stage(cap_rows, kin, kout));
         }
         if (frac >= 0.9) break;
     }
@@ -604,13 +633,29 @@ static int launch_bwd(EdgeBwdArgs a, const tecgat_plan_t *plan, int grid, cudaSt
     const size_t fixed = 128 + meta_bytes + red_bytes + out_bytes;
     const char *env = getenv("TECGAT_BWD_STAGES");
     const int want = env ? std::max(1, std::min(kMaxStages, atoi(env))) : 2;
-    const StagePickBwd sp = pick_stages_bwd(tl, g, fixed, want);
+    StagePickBwd sp = pick_stages_bwd(tl, g, fixed, want);
+    a.semi = 0;
+    {   // rows too wide for full staging (e.g. H*C = 44 on the 300 km graph): stage slab + stat + delta planes only
+        int full_tiles = 0;
+        for (int t = 0; t < tl.num_tiles; ++t) {
+            const tg_tile_meta &m = tl.h_meta[t];
+            full_tiles += sp.num_stages > 0 && m.eligible && m.hi - m.lo <= sp.cap_rows && (m.kin_kout & 0xFFFF) <= sp.cap_kin &&
+                          (m.kin_kout >> 16) <= sp.cap_kout;
+        }
+        if ((2 * full_tiles < tl.num_tiles || getenv("TECGAT_EDGE_SEMI")) && !getenv("TECGAT_EDGE_NOSTAGE")) {  // TECGAT_EDGE_SEMI: tests
+            const StagePickBwd ss = pick_stages_bwd(tl, g, fixed, want, true);
+            if (ss.num_stages > 0) {
+                sp = ss;
+                a.semi = 1;
+            }
+        }
+    }
     a.num_stages = sp.num_stages > 0 ? sp.num_stages : 1;
     a.cap_rows = sp.cap_rows;
     a.cap_kin = sp.num_stages > 0 ? sp.cap_kin : -1;
     if (getenv("TECGAT_EDGE_NOSTAGE")) a.cap_kin = -1;  // tests: force the gather-from-global path
     a.cap_kout = sp.cap_kout;
-    const size_t ybytes = g.win_f(a.cap_rows);
+    const size_t ybytes = a.semi ? 16 : g.win_f(a.cap_rows);
     a.off_meta = 128;
     a.off_red = (uint32_t)(128 + meta_bytes);
     a.off_y = (uint32_t)(a.off_red + red_bytes);
@@ -620,9 +665,15 @@ static int launch_bwd(EdgeBwdArgs a, const tecgat_plan_t *plan, int grid, cudaSt
     a.off_statraw = sp.off_statraw; a.off_ds = sp.off_ds; a.off_xl = sp.off_xl; a.off_xr = sp.off_xr; a.off_g = sp.off_g;
     const size_t smem = a.off_stage0 + size_t(sp.num_stages) * a.stage_bytes;
     TG_REQUIRE(smem <= 227 * 1024, TECGAT_ENOSUP, "edge_bwd: %zu B shared memory needed (tile %d x %d channels)", smem, T, HC);
-    auto kern = edge_bwd_kernel<C, ST, VEC, HT>;
-    TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)grid, (ncw + 1) * 32, smem, st>>>(a);
+    if (a.semi) {
+        auto kern = edge_bwd_kernel<C, ST, VEC, HT, true>;
+        TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)grid, (ncw + 1) * 32, smem, st>>>(a);
+    } else {
+        auto kern = edge_bwd_kernel<C, ST, VEC, HT, false>;
+        TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)grid, (ncw + 1) * 32, smem, st>>>(a);
+    }
     TG_LAUNCH_CHECK();
     return TECGAT_OK;
 }

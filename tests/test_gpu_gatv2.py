@@ -233,6 +233,19 @@ def test_gather_path_when_windows_are_not_staged(cuda_device, monkeypatch, S, N,
     _check(y, grads, y_ref, g_ref, TOL_F32, f"gather S{S}N{N}")
 
 
+@pytest.mark.parametrize("S,N,F,H,C,E", [(3, 300, 22, 2, 11, 3000), (2, 90, 5, 4, 3, 500), (2, 257, 10, 1, 5, 1200)])
+def test_backward_semi_staging(cuda_device, monkeypatch, S, N, F, H, C, E):
+    """Rows too wide for shared memory (H*C = 44 on the 300 km graph, see test_dense_graph_four_heads) stage only the ELL
+    slab and the (delta, stat) planes and gather xl / xr / g / y rows from L2; forced here on small graphs, with dropout."""
+    monkeypatch.setenv("TECGAT_EDGE_SEMI", "1")
+    ei = random_graph(N, E, seed=N + E + 11, isolated=(4,))
+    x, gy, p = _rand_case(S, N, F, H, C, seed=S * 7 + N)
+    enc = _encoder(F, H, C, p, cuda_device).eval()
+    y, grads = _run_cuda(enc, x, ei, gy)
+    y_ref, g_ref, _ = oracle_with_kernel_branches(x, ei, p, H, C, gy, cuda_device)
+    _check(y, grads, y_ref, g_ref, TOL_F32, f"semi S{S}N{N}")
+
+
 def test_softmax_shift_retry_on_huge_score_spread(cuda_device):
     """The kernels shift the softmax by the self-loop score; rows where another score exceeds it by more than ~2^100
     are redone with the exact maximum.  att scaled by 400 makes score differences of several hundred."""
