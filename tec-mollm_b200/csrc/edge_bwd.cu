@@ -197,7 +197,8 @@ __device__ __forceinline__ void bwd_lane(const CV<C> &attp, const CV<C> &attm, c
 
 // HT > 0: compile-time number of heads (address arithmetic folds); 0: runtime.  SEMI: the semi-staged variant (rows too
 // wide for shared memory) is a separate instantiation so that the fully staged kernel's code stays compact.
-template <int C, typename ST, bool VEC, int HT, bool SEMI>
+// GATHER: the launch contains tiles that are not staged (false drops the gather-from-global code: every item is staged).
+template <int C, typename ST, bool VEC, int HT, bool SEMI, bool GATHER>
 __global__ void __launch_bounds__(256, 1) edge_bwd_kernel(const EdgeBwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem);
@@ -240,7 +241,7 @@ __global__ void __launch_bounds__(256, 1) edge_bwd_kernel(const EdgeBwdArgs a) {
             const int n0 = tile * T, nt = min(N, n0 + T) - n0;
             const bool lit = a.literal && snap > 0;
             const int lo = lit ? n0 : m.lo, win = lit ? nt : m.hi - m.lo;
-            const bool staged = m.eligible && win <= a.cap_rows && (m.kin_kout & 0xFFFF) <= a.cap_kin && (m.kin_kout >> 16) <= a.cap_kout;
+            const bool staged = !GATHER || (m.eligible && win <= a.cap_rows && (m.kin_kout & 0xFFFF) <= a.cap_kin && (m.kin_kout >> 16) <= a.cap_kout);
             if (staged) {
                 const int64_t row0 = (int64_t)snap * N + lo;
                 unsigned char *stage = smem + a.off_stage0 + (size_t)ring.st * a.stage_bytes;
@@ -360,7 +361,7 @@ __global__ void __launch_bounds__(256, 1) edge_bwd_kernel(const EdgeBwdArgs a) {
         const int n0 = tile * T, nt = min(N, n0 + T) - n0;
         const bool lit = a.literal && snap > 0;
         const int lo = lit ? n0 : m.lo, win = lit ? nt : m.hi - m.lo;
-        const bool staged = m.eligible && win <= a.cap_rows && (m.kin_kout & 0xFFFF) <= a.cap_kin && (m.kin_kout >> 16) <= a.cap_kout;
+        const bool staged = !GATHER || (m.eligible && win <= a.cap_rows && (m.kin_kout & 0xFFFF) <= a.cap_kin && (m.kin_kout >> 16) <= a.cap_kout);
         const bool active = head_ok && node_l < nt;
         const int64_t row = (int64_t)snap * N + n0 + node_l;
         if (a.drop_thr && snap != key_snap) {
@@ -480,7 +481,7 @@ __global__ void __launch_bounds__(256, 1) edge_bwd_kernel(const EdgeBwdArgs a) {
                 }
             }
             __syncwarp();
-        } else {
+        } else if constexpr (GATHER) {
             // ---- window too large for a stage: everything straight from global memory (L2) --------------------------
             const int64_t snap0 = (int64_t)snap * N;
             const ST *xl_snap = static_cast<const ST *>(a.xl) + snap0 * HC + hh * C;
@@ -665,15 +666,21 @@ static int launch_bwd(EdgeBwdArgs a, const tecgat_plan_t *plan, int grid, cudaSt
     a.off_statraw = sp.off_statraw; a.off_ds = sp.off_ds; a.off_xl = sp.off_xl; a.off_xr = sp.off_xr; a.off_g = sp.off_g;
     const size_t smem = a.off_stage0 + size_t(sp.num_stages) * a.stage_bytes;
     TG_REQUIRE(smem <= 227 * 1024, TECGAT_ENOSUP, "edge_bwd: %zu B shared memory needed (tile %d x %d channels)", smem, T, HC);
-    if (a.semi) {
-        auto kern = edge_bwd_kernel<C, ST, VEC, HT, true>;
-        TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<(unsigned)grid, (ncw + 1) * 32, smem, st>>>(a);
-    } else {
-        auto kern = edge_bwd_kernel<C, ST, VEC, HT, false>;
-        TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<(unsigned)grid, (ncw + 1) * 32, smem, st>>>(a);
+    bool all_staged = a.cap_kin >= 0;
+    for (int t = 0; t < tl.num_tiles && all_staged; ++t) {
+        const tg_tile_meta &m = tl.h_meta[t];
+        all_staged = m.eligible && std::max(m.hi - m.lo, 0) <= a.cap_rows && (m.kin_kout & 0xFFFF) <= a.cap_kin && (m.kin_kout >> 16) <= a.cap_kout;
     }
+    auto go = [&](auto kern) -> int {
+        TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)grid, (ncw + 1) * 32, smem, st>>>(a);
+        return TECGAT_OK;
+    };
+    int rc;
+    if (a.semi) rc = go(edge_bwd_kernel<C, ST, VEC, HT, true, true>);
+    else if (HT > 0 && all_staged) rc = go(edge_bwd_kernel<C, ST, VEC, HT, false, HT == 0>);  // compact: no gather code
+    else rc = go(edge_bwd_kernel<C, ST, VEC, HT, false, true>);
+    if (rc != TECGAT_OK) return rc;
     TG_LAUNCH_CHECK();
     return TECGAT_OK;
 }

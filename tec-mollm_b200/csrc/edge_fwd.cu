@@ -121,7 +121,8 @@ __device__ __forceinline__ void fwd_lane(const EdgeFwdArgs &a, const CV<C> &attp
 }
 
 // HT > 0: compile-time number of heads (address arithmetic folds); 0: runtime
-template <int C, typename ST, bool VEC, int HT>
+// GATHER: the launch contains tiles that are not staged (false drops the gather-from-global code: every item is staged).
+template <int C, typename ST, bool VEC, int HT, bool GATHER>
 __global__ void __launch_bounds__(512, 1) edge_fwd_kernel(const EdgeFwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem);
@@ -157,7 +158,7 @@ __global__ void __launch_bounds__(512, 1) edge_fwd_kernel(const EdgeFwdArgs a) {
             const int n0 = tile * T, nt = min(N, n0 + T) - n0;
             const bool lit = a.literal && snap > 0;
             const int lo = lit ? n0 : m.lo, win = lit ? nt : m.hi - m.lo;
-            const bool staged = m.eligible && win <= a.cap_rows && (m.kin_kout & 0xFFFF) <= a.cap_k;
+            const bool staged = !GATHER || (m.eligible && win <= a.cap_rows && (m.kin_kout & 0xFFFF) <= a.cap_k);
             if (staged) {
                 unsigned char *stage = smem + a.off_stage0 + (size_t)ring.st * a.stage_bytes;
                 const WinCopy cr = win_copy(a.xr, (int64_t)snap * N + n0, nt, RB, a.per, Rtot);
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(512, 1) edge_fwd_kernel(const EdgeFwdArgs a) {
         const int n0 = tile * T, nt = min(N, n0 + T) - n0;
         const bool lit = a.literal && snap > 0;
         const int lo = lit ? n0 : m.lo, win = lit ? nt : m.hi - m.lo;
-        const bool staged = m.eligible && win <= a.cap_rows && (m.kin_kout & 0xFFFF) <= a.cap_k;
+        const bool staged = !GATHER || (m.eligible && win <= a.cap_rows && (m.kin_kout & 0xFFFF) <= a.cap_k);
         const bool active = head_ok && node_l < nt;
         const int64_t row = (int64_t)snap * N + n0 + node_l;
         if (a.drop_thr && snap != key_snap) {
@@ -250,7 +251,7 @@ __global__ void __launch_bounds__(512, 1) edge_fwd_kernel(const EdgeFwdArgs a) {
                 for (int i = lane; i < nv * HC; i += 32) y_g[i] = ybuf[i];
             }
             __syncwarp();
-        } else {
+        } else if constexpr (GATHER) {
             // window or degree too large for a stage: gather straight from global memory (L2)
             int deg = 0, k0 = 0;
             if (active) {
@@ -340,16 +341,27 @@ static int launch_fwd(EdgeFwdArgs a, const tecgat_plan_t *plan, cudaStream_t st)
     a.off_xr = sp.off_xr;
     a.off_xl = sp.off_xl;
     const size_t smem = a.off_stage0 + size_t(a.num_stages) * a.stage_bytes;
-    auto kern = edge_fwd_kernel<C, ST, VEC, HT>;
-    TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bool all_staged = a.cap_k >= 0;
+    for (int t = 0; t < tl.num_tiles && all_staged; ++t) {
+        const tg_tile_meta &m = tl.h_meta[t];
+        all_staged = m.eligible && m.hi - m.lo <= a.cap_rows && (m.kin_kout & 0xFFFF) <= a.cap_k;
+    }
     int dev = 0, sms = 0;
     TG_CUDA(cudaGetDevice(&dev));
     TG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    int occ = 1;
-    TG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, (ncw + 1) * 32, smem));
-    if (occ < 1) occ = 1;
-    const int64_t grid = std::min<int64_t>(a.items, int64_t(sms) * occ);
-    kern<<<(unsigned)grid, (ncw + 1) * 32, smem, st>>>(a);
+    auto go = [&](auto kern) -> int {
+        TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 1;
+        TG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, (ncw + 1) * 32, smem));
+        if (occ < 1) occ = 1;
+        const int64_t grid = std::min<int64_t>(a.items, int64_t(sms) * occ);
+        kern<<<(unsigned)grid, (ncw + 1) * 32, smem, st>>>(a);
+        return TECGAT_OK;
+    };
+    int rc;
+    if (HT > 0 && all_staged) rc = go(edge_fwd_kernel<C, ST, VEC, HT, HT == 0>);  // compact: no gather code
+    else rc = go(edge_fwd_kernel<C, ST, VEC, HT, true>);
+    if (rc != TECGAT_OK) return rc;
     TG_LAUNCH_CHECK();
     return TECGAT_OK;
 }
