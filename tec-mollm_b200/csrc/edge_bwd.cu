@@ -71,10 +71,12 @@ __device__ __forceinline__ void cv_axpy(CV<C> &y, float a, const CV<C> &x) {
     if (CV<C>::ODD) y.s = fmaf(a, x.s, y.s);
 }
 
+template <bool DROP>  // DROP = false: inference / p = 0 instantiation without the hash
 struct DropCfg {
     uint32_t thr, key;
     float inv_keep;
     __device__ __forceinline__ float q(uint32_t slot) const {
+        if (!DROP) return 1.f;
         // no branch on "dropout off": threshold 0 keeps every edge and inv_keep is 1 (the loop bodies stay one basic block)
         return dropout_bits(key, slot) >= thr ? inv_keep : 0.f;
     }
@@ -102,8 +104,8 @@ __device__ __forceinline__ float out_score(const CV<C> &attm, float c1, const CV
 // (slots past the degree read a valid row and get weight 0).
 //   NbrIn(k) / NbrOut(k): row index of the k-th in- / out-neighbour relative to the base pointers
 //   SlotOut(k): in-CSR slot (dropout counter) of the k-th out-edge;  DsOf(u, gu): (delta_u, stat_u)
-template <int C, typename ST, bool VEC, class NbrIn, class NbrOut, class SlotOut, class DsOf, class WaitDs>
-__device__ __forceinline__ void bwd_lane(const CV<C> &attp, const CV<C> &attm, const CV<C> &att, float slope, const DropCfg &drop,
+template <int C, typename ST, bool VEC, class Drop, class NbrIn, class NbrOut, class SlotOut, class DsOf, class WaitDs>
+__device__ __forceinline__ void bwd_lane(const CV<C> &attp, const CV<C> &attm, const CV<C> &att, float slope, const Drop &drop,
                                          const ST *xl_base, const ST *xr_base, const float *g_base, int HC, int par, ptrdiff_t vrow,
                                          float2 dv, int deg_in, int kmax_in, int deg_out, int kmax_out, uint32_t slot0,
                                          NbrIn nbr_in, NbrOut nbr_out, SlotOut slot_out, DsOf ds_of, WaitDs wait_ds, bool active, CV<C> &dxl,
@@ -198,7 +200,7 @@ __device__ __forceinline__ void bwd_lane(const CV<C> &attp, const CV<C> &attm, c
 // HT > 0: compile-time number of heads (address arithmetic folds); 0: runtime.  SEMI: the semi-staged variant (rows too
 // wide for shared memory) is a separate instantiation so that the fully staged kernel's code stays compact.
 // GATHER: the launch contains tiles that are not staged (false drops the gather-from-global code: every item is staged).
-template <int C, typename ST, bool VEC, int HT, bool SEMI, bool GATHER>
+template <int C, typename ST, bool VEC, int HT, bool SEMI, bool GATHER, bool DROP>
 __global__ void __launch_bounds__(256, 1) edge_bwd_kernel(const EdgeBwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem);
@@ -364,11 +366,11 @@ __global__ void __launch_bounds__(256, 1) edge_bwd_kernel(const EdgeBwdArgs a) {
         const bool staged = !GATHER || (m.eligible && win <= a.cap_rows && (m.kin_kout & 0xFFFF) <= a.cap_kin && (m.kin_kout >> 16) <= a.cap_kout);
         const bool active = head_ok && node_l < nt;
         const int64_t row = (int64_t)snap * N + n0 + node_l;
-        if (a.drop_thr && snap != key_snap) {
+        if (DROP && a.drop_thr && snap != key_snap) {
             key = dropout_snapshot_key(a.seed, (uint32_t)snap) ^ head_key;
             key_snap = snap;
         }
-        DropCfg drop;
+        DropCfg<DROP> drop;
         drop.thr = a.drop_thr;
         drop.key = key;
         drop.inv_keep = a.inv_keep;
@@ -677,9 +679,10 @@ static int launch_bwd(EdgeBwdArgs a, const tecgat_plan_t *plan, int grid, cudaSt
         return TECGAT_OK;
     };
     int rc;
-    if (a.semi) rc = go(edge_bwd_kernel<C, ST, VEC, HT, true, true>);
-    else if (HT > 0 && all_staged) rc = go(edge_bwd_kernel<C, ST, VEC, HT, false, HT == 0>);  // compact: no gather code
-    else rc = go(edge_bwd_kernel<C, ST, VEC, HT, false, true>);
+    if (a.semi) rc = go(edge_bwd_kernel<C, ST, VEC, HT, true, true, true>);
+    else if (HT > 0 && all_staged && a.drop_thr == 0) rc = go(edge_bwd_kernel<C, ST, VEC, HT, false, HT == 0, HT == 0>);  // inference: no hash either
+    else if (HT > 0 && all_staged) rc = go(edge_bwd_kernel<C, ST, VEC, HT, false, HT == 0, true>);  // compact: no gather code
+    else rc = go(edge_bwd_kernel<C, ST, VEC, HT, false, true, true>);
     if (rc != TECGAT_OK) return rc;
     TG_LAUNCH_CHECK();
     return TECGAT_OK;

@@ -40,7 +40,7 @@ struct EdgeFwdArgs {
 // The self loop (CSR slot 0) is peeled: it uses the lane's own xl row and its score is the softmax shift.  The other
 // slots are walked TWO per iteration, branch-free (slots past the lane's degree read a valid row and get weight 0), so
 // the two edges' instruction streams interleave.
-template <int C, typename ST, bool VEC, bool FAST>
+template <int C, typename ST, bool VEC, bool FAST, bool DROP>
 __device__ __forceinline__ void fwd_lane(const EdgeFwdArgs &a, const CV<C> &attp, const CV<C> &attm, const CV<C> &bias_h,
                                          const ST *xr_chunk, const ST *xl_self /* own row, + h*C */,
                                          const ST *xl_lane /* window row 0 (FAST) or snapshot row 0, + h*C */, int HC, int par,
@@ -67,6 +67,7 @@ __device__ __forceinline__ void fwd_lane(const EdgeFwdArgs &a, const CV<C> &attp
         return k < deg ? __ldg(col + k) : 0;
     };
     auto keep = [&](float w, int k) -> float {
+        if (!DROP) return w;  // inference / p = 0 instantiation: no hash
         // no branch on "dropout off": threshold 0 keeps every edge and inv_keep is 1, so the loop body stays ONE basic
         // block and the two edges of an iteration interleave freely
         return dropout_bits(key, slot0 + (uint32_t)k) >= a.drop_thr ? w * a.inv_keep : 0.f;
@@ -122,7 +123,7 @@ __device__ __forceinline__ void fwd_lane(const EdgeFwdArgs &a, const CV<C> &attp
 
 // HT > 0: compile-time number of heads (address arithmetic folds); 0: runtime
 // GATHER: the launch contains tiles that are not staged (false drops the gather-from-global code: every item is staged).
-template <int C, typename ST, bool VEC, int HT, bool GATHER>
+template <int C, typename ST, bool VEC, int HT, bool GATHER, bool DROP>
 __global__ void __launch_bounds__(512, 1) edge_fwd_kernel(const EdgeFwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem);
@@ -208,7 +209,7 @@ __global__ void __launch_bounds__(512, 1) edge_fwd_kernel(const EdgeFwdArgs a) {
         const bool staged = !GATHER || (m.eligible && win <= a.cap_rows && (m.kin_kout & 0xFFFF) <= a.cap_k);
         const bool active = head_ok && node_l < nt;
         const int64_t row = (int64_t)snap * N + n0 + node_l;
-        if (a.drop_thr && snap != key_snap) {
+        if (DROP && a.drop_thr && snap != key_snap) {
             key = dropout_snapshot_key(a.seed, (uint32_t)snap) ^ head_key;
             key_snap = snap;
         }
@@ -226,7 +227,7 @@ __global__ void __launch_bounds__(512, 1) edge_fwd_kernel(const EdgeFwdArgs a) {
             if (lit) deg = min(deg, 1);
             const uint32_t slot0 = active ? (uint32_t)k0s[node_l] : 0u;
             const int kmax_w = __reduce_max_sync(0xFFFFFFFFu, deg);
-            fwd_lane<C, ST, VEC, true>(a, attp, attm, bias_h, xr_s + node_l * HC + hh * C, xl_s + (n0 + node_l - lo) * HC + hh * C,
+            fwd_lane<C, ST, VEC, true, DROP>(a, attp, attm, bias_h, xr_s + node_l * HC + hh * C, xl_s + (n0 + node_l - lo) * HC + hh * C,
                                        xl_s + hh * C, HC, par, ell, nullptr, deg, kmax_w, slot0, key, out, stat);
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[ring.st]);  // this warp no longer reads the stage
@@ -262,7 +263,7 @@ __global__ void __launch_bounds__(512, 1) edge_fwd_kernel(const EdgeFwdArgs a) {
             const int kmax_w = __reduce_max_sync(0xFFFFFFFFu, deg);
             const ST *xl_snap = static_cast<const ST *>(a.xl) + (int64_t)snap * N * HC + hh * C;
             const ST *xr_chunk = static_cast<const ST *>(a.xr) + row * HC + hh * C;
-            fwd_lane<C, ST, VEC, false>(a, attp, attm, bias_h, xr_chunk, xl_snap + (int64_t)(n0 + node_l) * HC, xl_snap, HC, par, nullptr,
+            fwd_lane<C, ST, VEC, false, DROP>(a, attp, attm, bias_h, xr_chunk, xl_snap + (int64_t)(n0 + node_l) * HC, xl_snap, HC, par, nullptr,
                                         a.col + k0, deg, kmax_w, (uint32_t)k0, key, out, stat);
             if (active) cv_store<C, VEC>(a.y + row * HC + hh * C, out, par);
         }
@@ -359,8 +360,9 @@ static int launch_fwd(EdgeFwdArgs a, const tecgat_plan_t *plan, cudaStream_t st)
         return TECGAT_OK;
     };
     int rc;
-    if (HT > 0 && all_staged) rc = go(edge_fwd_kernel<C, ST, VEC, HT, HT == 0>);  // compact: no gather code
-    else rc = go(edge_fwd_kernel<C, ST, VEC, HT, true>);
+    if (HT > 0 && all_staged && a.drop_thr == 0) rc = go(edge_fwd_kernel<C, ST, VEC, HT, HT == 0, HT == 0>);  // inference: no hash either
+    else if (HT > 0 && all_staged) rc = go(edge_fwd_kernel<C, ST, VEC, HT, HT == 0, true>);  // compact: no gather code
+    else rc = go(edge_fwd_kernel<C, ST, VEC, HT, true, true>);
     if (rc != TECGAT_OK) return rc;
     TG_LAUNCH_CHECK();
     return TECGAT_OK;
