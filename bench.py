@@ -317,6 +317,8 @@ def run_gpu_arm(args):
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
+            line["other_configs"] = other_configs(enc, ei, gy, x, args, dev, E)
+        if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             times, edges = cpu_fwd_bwd_time(2, 3, 1, threads)
             best = min(times)
@@ -330,6 +332,48 @@ def run_gpu_arm(args):
         dist.barrier(device_ids=[local_rank])
         dist.destroy_process_group()
     return 0
+
+
+def other_configs(enc, ei, gy, x, args, dev, E):
+    """Secondary points of the same path, same run, untimed by the driver (BASELINE.json configs 1-2 run at B = 2 and config 2
+    under bf16 autocast): the other precision contract at this batch, and the reference's training batch B = 2."""
+    def timed(fn, n):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / n
+
+    def make(xin, gin, autocast):
+        def fn():
+            xin.grad = None
+            for p in enc.parameters():
+                p.grad = None
+            if autocast:
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    y = enc(xin, ei)
+            else:
+                y = enc(xin, ei)
+            y.backward(gin)
+        return fn
+
+    out = {}
+    other = not args.autocast
+    ms = timed(make(x, gy, other), 5)
+    out["bf16_autocast" if other else "fp32"] = {"batch_per_gpu": args.batch, "ms_per_step": ms,
+                                                  "edge_msgs_per_s": args.batch * L_IN * E / (ms * 1e-3)}
+    S2 = 2 * L_IN
+    x2 = torch.randn(S2, N_NODES, F_IN, device=dev).requires_grad_(True)
+    g2 = torch.randn(S2, N_NODES, HEADS * C_OUT, device=dev)
+    ms = timed(make(x2, g2, args.autocast), 50)
+    out["batch_2"] = {"batch_per_gpu": 2, "ms_per_step": ms, "edge_msgs_per_s": S2 * E / (ms * 1e-3), "samples_per_s": 2 / (ms * 1e-3),
+                      "note": "the reference's training batch (train.py:182): host-launch bound in eager mode, CUDA-graph capturable"}
+    return out
 
 
 def measured_traffic(kernel, rows, args):
