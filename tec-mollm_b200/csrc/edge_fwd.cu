@@ -41,7 +41,7 @@ struct EdgeFwdArgs {
 // slots are walked TWO per iteration, branch-free (slots past the lane's degree read a valid row and get weight 0), so
 // the two edges' instruction streams interleave.
 template <int C, typename ST, bool VEC, bool FAST, bool DROP>
-__device__ __forceinline__ void fwd_lane(const EdgeFwdArgs &a, const CV<C> &attp, const CV<C> &attm, const CV<C> &bias_h,
+__device__ __forceinline__ void fwd_lane(const EdgeFwdArgs &a, const CV<C> &attp, const CV<C> &attm, const float *bias_ptr,
                                          const ST *xr_chunk, const ST *xl_self /* own row, + h*C */,
                                          const ST *xl_lane /* window row 0 (FAST) or snapshot row 0, + h*C */, int HC, int par,
                                          const uint16_t *ell /* + node_l */, const int32_t *col /* + k0 */, int deg, int kmax_w,
@@ -115,6 +115,8 @@ __device__ __forceinline__ void fwd_lane(const EdgeFwdArgs &a, const CV<C> &attp
     }
     const float inv = l > 0.f ? __frcp_rn(l) : 0.f;
     const float2 inv2 = splat(inv);
+    CV<C> bias_h;  // read here (L1 hit) instead of living in 11 registers through the edge loop
+    cv_load_param<C>(bias_h, bias_ptr, par, 1.f);
 #pragma unroll
     for (int i = 0; i < CV<C>::NP; ++i) out.p[i] = __ffma2_rn(acc.p[i], inv2, bias_h.p[i]);
     out.s = fmaf(acc.s, inv, bias_h.s);
@@ -192,10 +194,10 @@ __global__ void __launch_bounds__(512, 1) edge_fwd_kernel(const EdgeFwdArgs a) {
     const bool head_ok = h < H;
     const int hh = head_ok ? h : 0;
     const int par = VEC ? ((hh * C) & 1) : 0;
-    CV<C> attp, attm, bias_h;
+    CV<C> attp, attm;
     cv_load_param<C>(attp, a.att + hh * C, par, 0.5f * (1.f + a.slope) * kLog2e);
     cv_load_param<C>(attm, a.att + hh * C, par, 0.5f * (1.f - a.slope) * kLog2e);
-    cv_load_param<C>(bias_h, a.bias + hh * C, par, 1.f);
+    const float *bias_h = a.bias + hh * C;
     float *ybuf = reinterpret_cast<float *>(smem + a.off_y) + warp * npw * HC;
     const uint32_t head_key = dropout_head_key((uint32_t)hh);
     uint32_t key = 0;
