@@ -232,13 +232,14 @@ __global__ void __launch_bounds__(256, 1) edge_bwd_kernel(const EdgeBwdArgs a) {
     __syncthreads();
     const ItemRange R = cta_items(a.items);
     int snap = (int)(R.w0 / a.num_tiles), tile = (int)(R.w0 % a.num_tiles);
+    const int n_items = (int)(R.w1 - R.w0);  // 32-bit loop counter (a CTA never owns 2^31 items)
     const int64_t Rtot = (int64_t)a.S * N;
     Ring ring{0, 0u};
     uint32_t yph = 0;  // phase parity of the single y window
 
     if (warp == ncw) {
         // ================================ producer warp ================================
-        for (int64_t w = R.w0; w < R.w1; ++w) {
+        for (int w = 0; w < n_items; ++w) {
             const tg_tile_meta m = load_meta(meta_s, a.meta, a.num_tiles, tile);
             const int n0 = tile * T, nt = min(N, n0 + T) - n0;
             const bool lit = a.literal && snap > 0;
@@ -358,7 +359,7 @@ __global__ void __launch_bounds__(256, 1) edge_bwd_kernel(const EdgeBwdArgs a) {
     ST *out_l = reinterpret_cast<ST *>(smem + a.off_out) + warp * npw * HC;               // d xl rows of this warp
     ST *out_r = reinterpret_cast<ST *>(smem + a.off_out) + (size_t)T * HC + warp * npw * HC;  // d xr rows
 
-    for (int64_t w = R.w0; w < R.w1; ++w) {
+    for (int w = 0; w < n_items; ++w) {
         const tg_tile_meta m = load_meta(meta_s, a.meta, a.num_tiles, tile);
         const int n0 = tile * T, nt = min(N, n0 + T) - n0;
         const bool lit = a.literal && snap > 0;

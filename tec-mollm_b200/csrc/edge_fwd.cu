@@ -151,12 +151,13 @@ __global__ void __launch_bounds__(512, 1) edge_fwd_kernel(const EdgeFwdArgs a) {
     __syncthreads();
     const ItemRange R = cta_items(a.items);
     int snap = (int)(R.w0 / a.num_tiles), tile = (int)(R.w0 % a.num_tiles);
+    const int n_items = (int)(R.w1 - R.w0);  // 32-bit loop counter (a CTA never owns 2^31 items)
     const int64_t Rtot = (int64_t)a.S * N;
     Ring ring{0, 0u};
 
     if (warp == ncw) {
         // ================================ producer warp ================================
-        for (int64_t w = R.w0; w < R.w1; ++w) {
+        for (int w = 0; w < n_items; ++w) {
             const tg_tile_meta m = load_meta(meta_s, a.meta, a.num_tiles, tile);
             const int n0 = tile * T, nt = min(N, n0 + T) - n0;
             const bool lit = a.literal && snap > 0;
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(512, 1) edge_fwd_kernel(const EdgeFwdArgs a) {
     uint32_t key = 0;
     int key_snap = -1;
 
-    for (int64_t w = R.w0; w < R.w1; ++w) {
+    for (int w = 0; w < n_items; ++w) {
         const tg_tile_meta m = load_meta(meta_s, a.meta, a.num_tiles, tile);
         const int n0 = tile * T, nt = min(N, n0 + T) - n0;
         const bool lit = a.literal && snap > 0;
