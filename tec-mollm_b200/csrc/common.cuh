@@ -220,12 +220,14 @@ __host__ __device__ __forceinline__ uint32_t dropout_head_key(uint32_t head) {  
 __host__ __device__ __forceinline__ uint32_t dropout_key(uint64_t seed, uint32_t snapshot, uint32_t head) {
     return dropout_snapshot_key(seed, snapshot) ^ dropout_head_key(head);
 }
-__host__ __device__ __forceinline__ uint32_t dropout_bits(uint32_t key, uint32_t slot) {
-    uint32_t h = slot * 0x9E3779B1u + key;
+constexpr uint32_t kDropMul = 0x9E3779B1u;
+// second half of the hash; `h` = slot * kDropMul + key (consecutive slots: h advances by kDropMul, one integer add)
+__host__ __device__ __forceinline__ uint32_t dropout_finish(uint32_t h) {
     h ^= h >> 15;
     h *= 0x85EBCA6Bu;
     return h;
 }
+__host__ __device__ __forceinline__ uint32_t dropout_bits(uint32_t key, uint32_t slot) { return dropout_finish(slot * kDropMul + key); }
 __host__ __device__ __forceinline__ uint32_t dropout_threshold(float p) {
     // keep iff bits >= thr;  P(drop) = thr / 2^32
     double t = static_cast<double>(p) * 4294967296.0;

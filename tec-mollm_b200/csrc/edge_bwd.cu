@@ -75,10 +75,11 @@ template <bool DROP>  // DROP = false: inference / p = 0 instantiation without t
 struct DropCfg {
     uint32_t thr, key;
     float inv_keep;
-    __device__ __forceinline__ float q(uint32_t slot) const {
+    __device__ __forceinline__ float q(uint32_t slot) const { return qh(slot * kDropMul + key); }
+    __device__ __forceinline__ float qh(uint32_t h) const {  // h = slot * kDropMul + key (consecutive slots: one add)
         if (!DROP) return 1.f;
         // no branch on "dropout off": threshold 0 keeps every edge and inv_keep is 1 (the loop bodies stay one basic block)
-        return dropout_bits(key, slot) >= thr ? inv_keep : 0.f;
+        return dropout_finish(h) >= thr ? inv_keep : 0.f;
     }
 };
 
@@ -137,8 +138,9 @@ __device__ __forceinline__ void bwd_lane(const CV<C> &attp, const CV<C> &attm, c
         cv_axpy<C>(G, alpha * q, g_v);
     }
     // ---- role 1: v as DESTINATION, in-edges (u -> v): A_in, B_in ------------------------------------------------
+    uint32_t hk = (slot0 + 1u) * kDropMul + drop.key;
 #pragma unroll 1
-    for (int k = 1; k < kmax_in; k += 2) {
+    for (int k = 1; k < kmax_in; k += 2, hk += 2u * kDropMul) {
         const ptrdiff_t ua = nbr_in(k), ub = nbr_in(k + 1);
         CV<C> xa, xb, sa, sb;
         cv_load<C, VEC>(xa, xl_base + ua * HC, par);
@@ -148,8 +150,8 @@ __device__ __forceinline__ void bwd_lane(const CV<C> &attp, const CV<C> &attm, c
         const float ga = cv_dot<C>(g_v, xa), gb = cv_dot<C>(g_v, xb);
         const float va = k < deg_in ? 1.f : 0.f, vb = k + 1 < deg_in ? 1.f : 0.f;
         const float aa = va * fast_exp2(fminf(ea - dv.y, 100.f)), ab = vb * fast_exp2(fminf(eb - dv.y, 100.f));
-        const float da = aa * fmaf(drop.q(slot0 + (uint32_t)k), ga, -dv.x);
-        const float db = ab * fmaf(drop.q(slot0 + (uint32_t)k + 1u), gb, -dv.x);
+        const float da = aa * fmaf(drop.qh(hk), ga, -dv.x);
+        const float db = ab * fmaf(drop.qh(hk + kDropMul), gb, -dv.x);
         A_in += da + db;
         acc_step<C>(B_in, sa, da);
         acc_step<C>(B_in, sb, db);

@@ -66,25 +66,27 @@ __device__ __forceinline__ void fwd_lane(const EdgeFwdArgs &a, const CV<C> &attp
         if (FAST) return (int)ell[k * Ts];
         return k < deg ? __ldg(col + k) : 0;
     };
-    auto keep = [&](float w, int k) -> float {
+    const uint32_t h0 = slot0 * kDropMul + key;  // hash input of slot k: h0 + k * kDropMul (one add per edge)
+    auto keep = [&](float w, uint32_t hk) -> float {
         if (!DROP) return w;  // inference / p = 0 instantiation: no hash
         // no branch on "dropout off": threshold 0 keeps every edge and inv_keep is 1, so the loop body stays ONE basic
         // block and the two edges of an iteration interleave freely
-        return dropout_bits(key, slot0 + (uint32_t)k) >= a.drop_thr ? w * a.inv_keep : 0.f;
+        return dropout_finish(hk) >= a.drop_thr ? w * a.inv_keep : 0.f;
     };
 #pragma unroll 1
     for (int attempt = 0; attempt < 2; ++attempt) {
         {
             const float w = wself * fast_exp2(e_self - shift);
             l = w;
-            const float wq = keep(w, 0);
+            const float wq = keep(w, h0);
             const float2 wq2 = splat(wq);
 #pragma unroll
             for (int i = 0; i < CV<C>::NP; ++i) acc.p[i] = __fmul2_rn(wq2, xl_i.p[i]);
             acc.s = wq * xl_i.s;
         }
+        uint32_t hk = h0 + kDropMul;
 #pragma unroll 1
-        for (int k = 1; k < kmax_w; k += 2) {
+        for (int k = 1; k < kmax_w; k += 2, hk += 2u * kDropMul) {
             const int ja = nbr(k), jb = nbr(k + 1);
             CV<C> xa, xb, sa, sb;
             cv_load<C, VEC>(xa, xl_lane + (FAST ? (ptrdiff_t)(ja * HC) : (ptrdiff_t)ja * HC), par);
@@ -97,7 +99,7 @@ __device__ __forceinline__ void fwd_lane(const EdgeFwdArgs &a, const CV<C> &attp
             const float wa = va * fast_exp2(fminf(ea - shift, 100.f));
             const float wb = vb * fast_exp2(fminf(eb - shift, 100.f));
             l += wa + wb;
-            const float2 qa = splat(keep(wa, k)), qb = splat(keep(wb, k + 1));
+            const float2 qa = splat(keep(wa, hk)), qb = splat(keep(wb, hk + kDropMul));
 #pragma unroll
             for (int i = 0; i < CV<C>::NP; ++i) acc.p[i] = __ffma2_rn(qb, xb.p[i], __ffma2_rn(qa, xa.p[i], acc.p[i]));
             if (CV<C>::ODD) acc.s = fmaf(qb.x, xb.s, fmaf(qa.x, xa.s, acc.s));
