@@ -114,6 +114,17 @@ int tecgat_edge_bwd(const tecgat_plan_t *plan, const void *xl_dev, const void *x
 int tecgat_dropout_mask_host(uint64_t seed, int64_t first_slot, int64_t count, int32_t heads,
                              float dropout_p, int64_t edges_per_snapshot, uint8_t *keep_host);
 
+/* ---- caller glue either side of the encoder: replaces the residual add and the
+ *      (L*B, N, C) -> (B, N, L, C) permute copy of TEC_MoLLM.forward (src/model/tec_mollm.py:94,100) with one
+ *      pass, and their autograd backward with one pass.  The permute of :84 needs no kernel: snapshots are
+ *      independent, so the encoder takes the (B, L, N, C) tensor as it is.  All tensors fp32, contiguous.
+ *        fwd:  z[b, n, l, :] = x[b, l, n, :] + y[b, l, n, :]     (y_dev may be NULL: pure transposition)
+ *        bwd:  g[b, l, n, :] = gz[b, n, l, :]                    (gradient of x's residual branch AND of y)  */
+int tecgat_residual_permute_fwd(const float *x_dev, const float *y_dev, float *z_dev, int32_t batch,
+                                int32_t steps, int32_t nodes, int32_t channels, void *stream);
+int tecgat_residual_permute_bwd(const float *gz_dev, float *g_dev, int32_t batch, int32_t steps,
+                                int32_t nodes, int32_t channels, void *stream);
+
 /* ---- graph builder: replaces calculate_haversine_distance_matrix (src/graph/graph_constructor.py:34-59,
  *      sklearn haversine_distances in fp64), construct_binary_adjacency (:61-81, inclusive `<=`, zero
  *      diagonal), symmetrically_normalize_adjacency (:99-128) and the COO extraction of

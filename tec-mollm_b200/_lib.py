@@ -37,6 +37,8 @@ _SIGNATURES = {
     "tecgat_edge_fwd": (C.c_int, [_vp] * 7 + [_i32, _i32, _i32, _f32, _f32, _u64, _i32, _i32, _vp]),
     "tecgat_edge_bwd_workspace": (_i64, [_vp, _i32, _i32, _i32]),
     "tecgat_edge_bwd": (C.c_int, [_vp] * 13 + [_i32, _i32, _i32, _f32, _f32, _u64, _i32, _i32, _vp]),
+    "tecgat_residual_permute_fwd": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "tecgat_residual_permute_bwd": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "tecgat_dropout_mask_host": (C.c_int, [_u64, _i64, _i64, _i32, _f32, _i64, _vp]),
     "tecgraph_distance_rows": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _f64, _vp, _vp]),
     "tecgraph_edges_count": (C.c_int, [_vp, _vp, _i64, _f64, _f64, _vp, C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_i64)]),

@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(kRows) project_fwd_ffma_kernel(const float *__
 
 // bwd.  shared: W_s[2HC][F] | d_s[kRows][2HC+1] | x_s[kRows][FP] | dx_s[kRows][FP]
 // per-thread parameter-gradient accumulators: outputs q = tid + i*kRows over [dW (2HC*F) | db (2HC)], i < kMaxAcc
-constexpr int kMaxAcc = 16;
+constexpr int kMaxAcc = 48;  // 6144 outputs: e.g. F = 44 with H*C = 44, or F = 64 with H*C = 44
 template <typename ST>
 __global__ void __launch_bounds__(kRows) project_bwd_ffma_kernel(const ST *__restrict__ dxl, const ST *__restrict__ dxr,
                                                                  const float *__restrict__ x, const float *__restrict__ wl,

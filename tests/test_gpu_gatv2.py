@@ -473,3 +473,45 @@ def test_four_dimensional_input_keeps_leading_dims(cuda_device):
     assert y4.shape == (B, L, N, H * C)
     y3 = enc(x4.permute(1, 0, 2, 3).reshape(L * B, N, F), ei)          # tec_mollm.py:84
     assert torch.equal(y3.view(L, B, N, H * C).permute(1, 0, 2, 3), y4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,L,H,C", [(2, 3, 2, 11), (3, 48, 2, 11), (2, 5, 1, 3), (1, 4, 4, 11)])
+def test_forward_block_equals_the_reference_glue(cuda_device, B, L, H, C):
+    """forward_block (fused residual + permute, tec_mollm.py:84-106) against the reference's own three lines run with
+    torch ops around the same encoder: bit-identical output and input gradient, equal parameter gradients."""
+    ei = torch.from_numpy(load_golden("graph_small150.npz")["edge_index"]).to(cuda_device)
+    N = int(ei.max().item()) + 1
+    F = H * C
+    x, _, p = _rand_case(B * L, N, F, H, C, seed=21, dtype=torch.float32)
+    enc = _encoder(F, H, C, p, cuda_device).eval()
+    gz = torch.randn(B * N, L, F, generator=torch.Generator().manual_seed(5)).to(cuda_device)
+    xa = x.view(B, L, N, F).to(cuda_device).requires_grad_(True)
+    za = enc.forward_block(xa, ei)
+    assert za.shape == (B * N, L, F)
+    za.backward(gz)
+    ga = {k: q.grad.clone() for k, q in enc.named_parameters()}
+    for q in enc.parameters():
+        q.grad = None
+    xb = x.view(B, L, N, F).to(cuda_device).requires_grad_(True)
+    x_for_gnn = xb.permute(1, 0, 2, 3).reshape(-1, N, F)                       # tec_mollm.py:84
+    x_spatial = x_for_gnn + enc(x_for_gnn, ei, None)                           # :89-94
+    zb = x_spatial.view(L, B, N, F).permute(1, 2, 0, 3).reshape(-1, L, F)      # :100-106
+    zb.backward(gz)
+    assert torch.equal(za, zb)
+    assert torch.equal(xa.grad, xb.grad)
+    for k, q in enc.named_parameters():  # the snapshots are summed in a different order (b*L + l instead of l*B + b)
+        assert rel_err(ga[k], q.grad) <= 2e-6, k
+
+
+@pytest.mark.gpu
+def test_forward_block_rejects_bad_input(cuda_device):
+    from tec_mollm_b200 import SpatialEncoder
+    enc = SpatialEncoder(22, 11, heads=2).to(cuda_device)
+    ei = torch.tensor([[0, 1], [1, 0]], device=cuda_device)
+    with pytest.raises(ValueError):
+        enc.forward_block(torch.zeros(2, 3, 22, device=cuda_device), ei)
+    with pytest.raises(ValueError):
+        enc.forward_block(torch.zeros(1, 2, 3, 10, device=cuda_device), ei)
+    with pytest.raises(RuntimeError):
+        enc.forward_block(torch.zeros(1, 2, 3, 22), ei.cpu())
