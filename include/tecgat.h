@@ -89,6 +89,15 @@ int tecgat_project_bwd(const void *dxl_dev, const void *dxr_dev, const float *x_
                        int64_t rows, int32_t in_channels, int32_t hc, int32_t dtype, int32_t impl,
                        void *stream);
 
+/* dx += dxl Wl + dxr Wr (dx_dev pre-loaded by the caller, e.g. with the residual branch's gradient from
+ * tecgat_residual_permute_bwd: replaces autograd's separate accumulation pass); otherwise as tecgat_project_bwd
+ * with impl = TECGAT_PROJ_TC and the same workspace.  tecgat_project_bwd_acc_supported: 1 when (F, hc) is in range. */
+int tecgat_project_bwd_acc_supported(int32_t in_channels, int32_t hc);
+int tecgat_project_bwd_acc(const void *dxl_dev, const void *dxr_dev, const float *x_dev,
+                           const float *wl_dev, const float *wr_dev, float *dx_dev, float *dwl_dev,
+                           float *dbl_dev, float *dwr_dev, float *dbr_dev, void *workspace_dev,
+                           int64_t rows, int32_t in_channels, int32_t hc, int32_t dtype, void *stream);
+
 /* ---- fused edge phase: replaces gather + LeakyReLU*att + segment softmax + dropout + scatter-add
  *      + bias (~20 ATen launches in PyG) with one kernel over all snapshots.
  *      dropout_p == 0 disables dropout; otherwise the keep bit of (snapshot s, CSR slot k, head h) is the

@@ -34,6 +34,8 @@ _SIGNATURES = {
     "tecgat_project_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp]),
     "tecgat_project_bwd_workspace": (_i64, [_i64, _i32, _i32, _i32]),
     "tecgat_project_bwd": (C.c_int, [_vp] * 11 + [_i64, _i32, _i32, _i32, _i32, _vp]),
+    "tecgat_project_bwd_acc_supported": (C.c_int, [_i32, _i32]),
+    "tecgat_project_bwd_acc": (C.c_int, [_vp] * 11 + [_i64, _i32, _i32, _i32, _vp]),
     "tecgat_edge_fwd": (C.c_int, [_vp] * 7 + [_i32, _i32, _i32, _f32, _f32, _u64, _i32, _i32, _vp]),
     "tecgat_edge_bwd_workspace": (_i64, [_vp, _i32, _i32, _i32]),
     "tecgat_edge_bwd": (C.c_int, [_vp] * 13 + [_i32, _i32, _i32, _f32, _f32, _u64, _i32, _i32, _vp]),

@@ -149,6 +149,12 @@ __device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, u
                  "r"(smem_u32(src_smem)), "r"(bytes)
                  : "memory");
 }
+// bulk reduction: global fp32 += shared fp32, element-wise, performed at the L2 (one add per element: deterministic)
+__device__ __forceinline__ void bulk_s2g_add_f32(void *dst_gmem, const void *src_smem, uint32_t bytes) {
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst_gmem),
+                 "r"(smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }

@@ -43,3 +43,24 @@ extern "C" int tecgat_project_bwd(const void *dxl, const void *dxr, const float 
         return tg::project_bwd_rt(dxl, dxr, x, wl, wr, dx, dwl, dbl, dwr, dbr, workspace, rows, F, hc, dtype, st);
     return tg::project_bwd_tc(dxl, dxr, x, wl, wr, dx, dwl, dbl, dwr, dbr, workspace, rows, F, hc, dtype, st);
 }
+
+// dx += dxl Wl + dxr Wr: the caller pre-loaded dx (the spatial block's residual-branch gradient, permute.cu), so autograd's
+// separate accumulation pass disappears.  Only the register-tiled kernel implements it (a bulk-TMA reduction store).
+extern "C" int tecgat_project_bwd_acc_supported(int32_t F, int32_t hc) {
+    const char *env = getenv("TECGAT_PROJ_BWD");
+    if (env && env[0] == 't') return 0;
+    return tg::project_bwd_rt_supported(F, hc, nullptr, nullptr, nullptr, nullptr) ? 1 : 0;
+}
+
+extern "C" int tecgat_project_bwd_acc(const void *dxl, const void *dxr, const float *x, const float *wl, const float *wr,
+                                      float *dx, float *dwl, float *dbl, float *dwr, float *dbr, void *workspace,
+                                      int64_t rows, int32_t F, int32_t hc, int32_t dtype, void *stream) {
+    TG_REQUIRE(dxl && dxr && x && wl && wr && dx && dwl && dbl && dwr && dbr && workspace, TECGAT_EINVAL, "project_bwd_acc: NULL argument");
+    TG_REQUIRE(rows > 0 && F > 0 && hc > 0, TECGAT_EINVAL, "project_bwd_acc: non-positive size");
+    TG_REQUIRE(dtype == TECGAT_F32 || dtype == TECGAT_BF16, TECGAT_EINVAL, "project_bwd_acc: bad dtype %d", dtype);
+    TG_REQUIRE(tg::project_bwd_rt_supported(F, hc, dxl, dxr, x, dx), TECGAT_ENOSUP,
+               "project_bwd_acc: F=%d, H*C=%d (or a pointer that is not 16-byte aligned) is outside the accumulating kernel's range; "
+               "call tecgat_project_bwd and add", F, hc);
+    return tg::project_bwd_rt(dxl, dxr, x, wl, wr, dx, dwl, dbl, dwr, dbr, workspace, rows, F, hc, dtype,
+                              static_cast<cudaStream_t>(stream), true);
+}

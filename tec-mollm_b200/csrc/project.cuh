@@ -22,5 +22,6 @@ int project_bwd_tc(const void *dxl, const void *dxr, const float *x, const float
 bool project_bwd_rt_supported(int F, int HC, const void *dxl, const void *dxr, const void *x, const void *dx);
 int64_t project_bwd_rt_workspace(int64_t R, int F, int HC);
 int project_bwd_rt(const void *dxl, const void *dxr, const float *x, const float *wl, const float *wr, float *dx, float *dwl,
-                   float *dbl, float *dwr, float *dbr, void *workspace, int64_t R, int F, int HC, int dtype, cudaStream_t st);
+                   float *dbl, float *dwr, float *dbr, void *workspace, int64_t R, int F, int HC, int dtype, cudaStream_t st,
+                   bool accumulate = false);
 }  // namespace tg

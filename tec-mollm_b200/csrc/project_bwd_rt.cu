@@ -43,6 +43,7 @@ struct Args {
     const void *dxl, *dxr;
     const float *x, *wl, *wr;
     float *dx;        // may be NULL
+    int32_t accumulate;  // dx += (the caller pre-loaded dx, e.g. with a residual branch's gradient) instead of dx =
     float *partials;  // (grid, 2*HC*F + 2*HC): [dWl | dWr | dbl | dbr] per CTA
     int64_t R;
     int32_t F, HC;
@@ -212,11 +213,12 @@ __global__ void __launch_bounds__(kThreads, 1) project_bwd_rt_kernel(const Args 
             float *gdx = a.dx + r0 * F;
             if (nr == kRows) {
                 if (tw == 0 && lane == 0) {
-                    bulk_s2g(gdx, dxst, kRows * F * 4u);
+                    if (a.accumulate) bulk_s2g_add_f32(gdx, dxst, kRows * F * 4u);
+                    else bulk_s2g(gdx, dxst, kRows * F * 4u);
                     bulk_commit();
                 }
             } else {
-                for (int i = tw * 32 + lane; i < nr * F; i += 64) gdx[i] = dxst[i];
+                for (int i = tw * 32 + lane; i < nr * F; i += 64) gdx[i] = a.accumulate ? gdx[i] + dxst[i] : dxst[i];
             }
         }
         if (need_dx && tw == 0 && lane == 0) bulk_wait0();
@@ -309,8 +311,10 @@ bool project_bwd_rt_supported(int F, int HC, const void *dxl, const void *dxr, c
 int64_t project_bwd_rt_workspace(int64_t R, int F, int HC) { return int64_t(rt::grid_for(R)) * (2 * HC * F + 2 * HC) * (int64_t)sizeof(float); }
 
 int project_bwd_rt(const void *dxl, const void *dxr, const float *x, const float *wl, const float *wr, float *dx, float *dwl,
-                   float *dbl, float *dwr, float *dbr, void *workspace, int64_t R, int F, int HC, int dtype, cudaStream_t st) {
+                   float *dbl, float *dwr, float *dbr, void *workspace, int64_t R, int F, int HC, int dtype, cudaStream_t st,
+                   bool accumulate) {
     rt::Args a;
+    a.accumulate = accumulate ? 1 : 0;
     a.dxl = dxl; a.dxr = dxr; a.x = x; a.wl = wl; a.wr = wr; a.dx = dx; a.partials = static_cast<float *>(workspace);
     a.R = R; a.F = F; a.HC = HC;
     const int grid = rt::grid_for(R);

@@ -120,7 +120,9 @@ class _GATv2Function(torch.autograd.Function):
     fixed-order reductions).  Saved for backward: x, xl, xr, y, stat (PyG saves 4-6 (S*E, H, C) tensors)."""
 
     @staticmethod
-    def forward(ctx, x2d, wl, bl, wr, br, att, bias, plan: GraphPlan, S, H, Cc, slope, p, seed, mode, dtype, impl):
+    def forward(ctx, x2d, wl, bl, wr, br, att, bias, plan: GraphPlan, S, H, Cc, slope, p, seed, mode, dtype, impl, block=None):
+        # block = (B, L): x2d is the (B, L, N, F) tensor flattened; return the whole spatial block of tec_mollm.py:84-106,
+        # z[b, n, l, :] = x[b, l, n, :] + y[b, l, n, :], instead of y (SURVEY.md 8f N1)
         dev = x2d.device
         R, F = x2d.shape
         HC = H * Cc
@@ -138,10 +140,16 @@ class _GATv2Function(torch.autograd.Function):
             _lib.call("tecgat_edge_fwd", plan.handle, _ptr(xl), _ptr(xr), _ptr(att), _ptr(bias), _ptr(y), _ptr(stat),
                       S, H, Cc, slope, p, seed, mode, dtype, stream)
             _mark("edge_fwd", dev)
+            out = y
+            if block is not None:
+                B, L = block
+                out = torch.empty((B, R // S, L, HC), device=dev, dtype=torch.float32)
+                _lib.call("tecgat_residual_permute_fwd", _ptr(x2d), _ptr(y), _ptr(out), B, L, R // S, HC, stream)
         ctx.save_for_backward(x2d, wl, wr, att, bias, xl, xr, y, stat)
         ctx.plan = plan
         ctx.cfg = (S, H, Cc, slope, p, seed, mode, dtype, impl)
-        return y
+        ctx.block = block
+        return out
 
     @staticmethod
     def backward(ctx, gy):
@@ -154,17 +162,28 @@ class _GATv2Function(torch.autograd.Function):
         gy = gy.contiguous()
         if gy.dtype != torch.float32:
             gy = gy.float()
-        if gy.data_ptr() % 16:  # bulk-TMA sources are 16-byte aligned
+        block = ctx.block
+        if block is None and gy.data_ptr() % 16:  # bulk-TMA sources are 16-byte aligned
             gy = gy.clone()
         with torch.cuda.device(dev):  # autograd worker threads do not inherit the current device
             stream = _stream(dev)
+            if block is not None:  # gy arrives as (B, N, L, HC): one transposition gives the gradient of y AND of the residual
+                B, L = block
+                g = torch.empty((R, HC), device=dev, dtype=torch.float32)
+                _lib.call("tecgat_residual_permute_bwd", _ptr(gy), _ptr(g), B, L, R // S, HC, stream)
+                gy = g
             dxl = torch.empty_like(xl)
             dxr = torch.empty_like(xr)
             datt = torch.empty((1, H, Cc), device=dev, dtype=torch.float32)
             dbias = torch.empty((HC,), device=dev, dtype=torch.float32)
             ws1 = torch.empty((max(1, _lib.lib().tecgat_edge_bwd_workspace(plan.handle, S, H, Cc)),), device=dev,
                               dtype=torch.uint8)
-            dx = torch.empty_like(x2d) if ctx.needs_input_grad[0] else None
+            dx = torch.empty_like(x2d) if ctx.needs_input_grad[0] and block is None else None
+            # block: dx = g + dxl Wl + dxr Wr accumulates in place into g (nobody reads gy after edge_bwd)
+            acc = (block is not None and ctx.needs_input_grad[0] and impl == _lib.PROJ_TC
+                   and _lib.lib().tecgat_project_bwd_acc_supported(F, HC) == 1)
+            if block is not None and ctx.needs_input_grad[0] and not acc:
+                dx = torch.empty_like(x2d)
             dwl = torch.empty_like(wl)
             dwr = torch.empty_like(wr)
             dbl = torch.empty((HC,), device=dev, dtype=torch.float32)
@@ -176,10 +195,17 @@ class _GATv2Function(torch.autograd.Function):
                       _ptr(gy), _ptr(dxl), _ptr(dxr), _ptr(datt), _ptr(dbias), _ptr(ws1), S, H, Cc, slope, p,
                       seed, mode, dtype, stream)
             _mark("edge_bwd", dev)
-            _lib.call("tecgat_project_bwd", _ptr(dxl), _ptr(dxr), _ptr(x2d), _ptr(wl), _ptr(wr), _ptr(dx), _ptr(dwl),
-                      _ptr(dbl), _ptr(dwr), _ptr(dbr), _ptr(ws2), R, F, HC, dtype, impl, stream)
+            if acc:
+                _lib.call("tecgat_project_bwd_acc", _ptr(dxl), _ptr(dxr), _ptr(x2d), _ptr(wl), _ptr(wr), _ptr(gy), _ptr(dwl),
+                          _ptr(dbl), _ptr(dwr), _ptr(dbr), _ptr(ws2), R, F, HC, dtype, stream)
+                dx = gy
+            else:
+                _lib.call("tecgat_project_bwd", _ptr(dxl), _ptr(dxr), _ptr(x2d), _ptr(wl), _ptr(wr), _ptr(dx), _ptr(dwl),
+                          _ptr(dbl), _ptr(dwr), _ptr(dbr), _ptr(ws2), R, F, HC, dtype, impl, stream)
+                if block is not None and dx is not None:
+                    dx += gy
             _mark("proj_bwd", dev)
-        return (dx, dwl, dbl, dwr, dbr, datt, dbias) + (None,) * 10
+        return (dx, dwl, dbl, dwr, dbr, datt, dbias) + (None,) * 11
 
 
 class _Linear(nn.Module):
@@ -270,9 +296,10 @@ class GATv2Conv(nn.Module):
         return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
 
     def forward_snapshots(self, x: torch.Tensor, edge_index: torch.Tensor, snapshots: int, num_nodes: int,
-                          snapshot_mode: str = "shared", seed: Optional[int] = None) -> torch.Tensor:
+                          snapshot_mode: str = "shared", seed: Optional[int] = None, block=None) -> torch.Tensor:
         """``x``: (snapshots*num_nodes, in_channels); the one-graph ``edge_index`` (indices < num_nodes) is
-        applied per ``snapshot_mode``.  Returns (snapshots*num_nodes, heads*out_channels) fp32."""
+        applied per ``snapshot_mode``.  Returns (snapshots*num_nodes, heads*out_channels) fp32; with ``block=(B, L)``
+        (snapshots = B*L laid out (B, L)) the whole spatial block ``(B, num_nodes, L, heads*out_channels)``."""
         if not x.is_cuda:
             raise RuntimeError("tec_mollm_b200.GATv2Conv: input must be a CUDA tensor (there is no CPU fallback)")
         if x.dim() != 2 or x.size(1) != self.in_channels or x.size(0) != snapshots * num_nodes:
@@ -297,7 +324,7 @@ class GATv2Conv(nn.Module):
         return _GATv2Function.apply(
             x, f32(self.lin_l.weight), f32(self.lin_l.bias), f32(self.lin_r.weight), f32(self.lin_r.bias),
             f32(self.att), f32(self.bias), plan, int(snapshots), self.heads, self.out_channels,
-            self.negative_slope, float(p), int(seed or 0), mode, dtype, _proj_impl())
+            self.negative_slope, float(p), int(seed or 0), mode, dtype, _proj_impl(), block)
 
     def forward(self, x: torch.Tensor, edge_index: torch.Tensor, edge_attr=None, return_attention_weights=None):
         """PyG semantics for one 2-D input: ``num_nodes = x.size(0)`` rows, edges as given (so calling it the way

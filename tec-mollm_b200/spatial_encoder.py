@@ -17,33 +17,7 @@ import logging
 import torch
 from torch import nn
 
-from . import _lib
 from .gatv2 import GATv2Conv
-
-
-class _ResidualPermute(torch.autograd.Function):
-    """``z[b, n, l, :] = x[b, l, n, :] + y[b, l, n, :]`` in one pass (tec_mollm.py:94,100); the backward is one
-    transposition whose result is the gradient of both inputs."""
-
-    @staticmethod
-    def forward(ctx, x, y):
-        B, L, N, Cc = x.shape
-        z = torch.empty(B, N, L, Cc, device=x.device, dtype=torch.float32)
-        with torch.cuda.device(x.device):
-            st = torch.cuda.current_stream(x.device).cuda_stream
-            _lib.call("tecgat_residual_permute_fwd", x.data_ptr(), y.data_ptr(), z.data_ptr(), B, L, N, Cc, st)
-        ctx.shape = (B, L, N, Cc)
-        return z
-
-    @staticmethod
-    def backward(ctx, gz):
-        B, L, N, Cc = ctx.shape
-        gz = gz.contiguous().float()
-        g = torch.empty(B, L, N, Cc, device=gz.device, dtype=torch.float32)
-        with torch.cuda.device(gz.device):  # the autograd worker thread: no thread-local CUDA state is assumed
-            st = torch.cuda.current_stream(gz.device).cuda_stream
-            _lib.call("tecgat_residual_permute_bwd", gz.data_ptr(), g.data_ptr(), B, L, N, Cc, st)
-        return g, g
 
 
 class SpatialEncoder(nn.Module):
@@ -86,15 +60,17 @@ class SpatialEncoder(nn.Module):
             x_spatial.view(L, B, N, C).permute(1, 2, 0, 3).reshape(-1, L, C)
 
         without the permute copy of :84 (the encoder reads the snapshots where they lie) and with the residual add and
-        the permute of :94-100 fused into one pass (one pass in backward too).  Dropout draws differ from the three-line
-        form only in which snapshot gets which counter."""
+        the permute of :94-100 fused into one pass; in backward one transposition yields the gradient of both branches and
+        the projection's backward accumulates ``dx`` into it in place.  Dropout draws differ from the three-line form only in
+        which snapshot gets which counter."""
         if x.dim() != 4:
             raise ValueError(f"x must be (B, L, N, C); got {tuple(x.shape)}")
         if x.size(-1) != self.output_channels:
             raise ValueError(f"the residual needs in_channels == heads*out_channels; got {x.size(-1)} vs {self.output_channels}")
         if not x.is_cuda:
             raise RuntimeError("SpatialEncoder.forward_block needs CUDA tensors (there is no CPU path)")
+        if self.snapshot_mode != "shared":
+            raise ValueError("forward_block implements the shared-graph semantics only")
         B, L, N, Cc = x.shape
-        xc = x.contiguous().float()
-        y = self.forward(xc, edge_index, edge_weight)
-        return _ResidualPermute.apply(xc, y.float().contiguous()).view(B * N, L, Cc)
+        z = self.gat_conv.forward_snapshots(x.reshape(-1, Cc), edge_index, B * L, N, "shared", block=(B, L))
+        return z.view(B * N, L, Cc)

@@ -64,8 +64,8 @@ def main():
         rows = B * L * N
         print(json.dumps({"what": "spatial_block_fwd_bwd", "B": B, "ms_encoder_only": t_bare, "ms_reference_glue": t_glue,
                           "ms_forward_block": t_fused, "glue_overhead_ms": t_glue - t_bare, "fused_overhead_ms": t_fused - t_bare,
-                          "fused_glue_GBps": rows * F * 4 * 8 / ((t_fused - t_bare) * 1e-3) / 1e9,
-                          "note": "fused glue moves 8 x C x 4 B/row: fwd 3 (x, y, z), bwd transposition 2, autograd's dx accumulation 3"}))
+                          "fused_glue_GBps": rows * F * 4 * 6 / ((t_fused - t_bare) * 1e-3) / 1e9,
+                          "note": "fused glue moves 6 x C x 4 B/row: fwd 3 (x, y, z), bwd transposition 2, +1 read for dx accumulating in place (bulk reduction store)"}))
         del enc, x, gz, gz_bl
         torch.cuda.empty_cache()
 
