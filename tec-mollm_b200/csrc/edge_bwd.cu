@@ -202,8 +202,12 @@ __device__ __forceinline__ void bwd_lane(const CV<C> &attp, const CV<C> &attm, c
 // HT > 0: compile-time number of heads (address arithmetic folds); 0: runtime.  SEMI: the semi-staged variant (rows too
 // wide for shared memory) is a separate instantiation so that the fully staged kernel's code stays compact.
 // GATHER: the launch contains tiles that are not staged (false drops the gather-from-global code: every item is staged).
-template <int C, typename ST, bool VEC, int HT, bool SEMI, bool GATHER, bool DROP>
-__global__ void __launch_bounds__(256, 1) edge_bwd_kernel(const EdgeBwdArgs a) {
+// WG: 384-thread CTA = 8 consumer warps (two warpgroups) + one producer warpgroup; the producer group hands its registers to
+// the consumers (setmaxnreg), which lifts the consumers to 8 warps x 240 registers -- the register file's split per scheduler
+// (16 K registers each) would otherwise cap a 9-warp CTA at 168 registers per thread.
+constexpr int kWgConsumerRegs = 232, kWgProducerRegs = 40;
+template <int C, typename ST, bool VEC, int HT, bool SEMI, bool GATHER, bool DROP, bool WG = false>
+__global__ void __launch_bounds__(WG ? 384 : 256, 1) edge_bwd_kernel(const EdgeBwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem);
     uint64_t *empty = full + kMaxStages;
@@ -212,7 +216,7 @@ __global__ void __launch_bounds__(256, 1) edge_bwd_kernel(const EdgeBwdArgs a) {
     uint64_t *dready = yempty + 1;  // per stage: every consumer warp has written its share of the (delta, stat) planes
     const tg_tile_meta *meta_s = reinterpret_cast<const tg_tile_meta *>(smem + a.off_meta);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ncw = (blockDim.x >> 5) - 1;
+    const int ncw = WG ? 8 : (blockDim.x >> 5) - 1;
     const int nct = ncw * 32;  // consumer threads
     const int H = HT > 0 ? HT : a.H, HC = H * C, T = a.T, N = a.N;
     const int Ts = (T + 7) & ~7;  // row stride of the slab sections
@@ -239,8 +243,15 @@ __global__ void __launch_bounds__(256, 1) edge_bwd_kernel(const EdgeBwdArgs a) {
     Ring ring{0, 0u};
     uint32_t yph = 0;  // phase parity of the single y window
 
-    if (warp == ncw) {
+    if (warp >= ncw) {
         // ================================ producer warp ================================
+        if (WG) {
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kWgProducerRegs));
+            if (warp > ncw + 1 || (SEMI && warp > ncw)) return;  // the group's remaining warps only donate their registers
+        }
+        // WG: two producer warps -- `ncw` streams the stages, `ncw + 1` the single y window (gated by the consumers' delta
+        // pre-pass, not by a stage): neither waits on the other's barrier, and each keeps few values live in its 40 registers
+        const bool do_stage = !WG || warp == ncw, do_y = !WG || warp == ncw + 1;
         for (int w = 0; w < n_items; ++w) {
             const tg_tile_meta m = load_meta(meta_s, a.meta, a.num_tiles, tile);
             const int n0 = tile * T, nt = min(N, n0 + T) - n0;
@@ -264,36 +275,40 @@ __global__ void __launch_bounds__(256, 1) edge_bwd_kernel(const EdgeBwdArgs a) {
                         if (c3.mid) bulk_g2s(stage + a.off_statraw, c3.src, c3.mid, &full[ring.st]);
                     }
                 } else {
-                const WinCopy c0 = win_copy(a.xl, row0, win, RB_ST, a.per_st, Rtot);
-                const WinCopy c1 = win_copy(a.xr, row0, win, RB_ST, a.per_st, Rtot);
-                const WinCopy c2 = win_copy(a.gy, row0, win, RB_F, a.per_f, Rtot);
-                const WinCopy c4 = win_copy(a.y, row0, win, RB_F, a.per_f, Rtot);
-                if (lane == 0) mbar_wait(&empty[ring.st], ring.ph ^ 1u);
-                __syncwarp();
-                if (c0.tail | c1.tail | c2.tail | c3.tail) {  // only the last rows of the last snapshot
-                    win_copy_tail(c0, stage + a.off_xl, lane);
-                    win_copy_tail(c1, stage + a.off_xr, lane);
-                    win_copy_tail(c2, stage + a.off_g, lane);
-                    win_copy_tail(c3, stage + a.off_statraw, lane);
+                if (do_stage) {
+                    const WinCopy c0 = win_copy(a.xl, row0, win, RB_ST, a.per_st, Rtot);
+                    const WinCopy c1 = win_copy(a.xr, row0, win, RB_ST, a.per_st, Rtot);
+                    const WinCopy c2 = win_copy(a.gy, row0, win, RB_F, a.per_f, Rtot);
+                    if (lane == 0) mbar_wait(&empty[ring.st], ring.ph ^ 1u);
                     __syncwarp();
+                    if (c0.tail | c1.tail | c2.tail | c3.tail) {  // only the last rows of the last snapshot
+                        win_copy_tail(c0, stage + a.off_xl, lane);
+                        win_copy_tail(c1, stage + a.off_xr, lane);
+                        win_copy_tail(c2, stage + a.off_g, lane);
+                        win_copy_tail(c3, stage + a.off_statraw, lane);
+                        __syncwarp();
+                    }
+                    if (lane == 0) {
+                        mbar_arrive_expect_tx(&full[ring.st], (uint32_t)m.slab_bytes + c0.mid + c1.mid + c2.mid + c3.mid);
+                        bulk_g2s(stage, a.slabs + m.slab_off, (uint32_t)m.slab_bytes, &full[ring.st]);
+                        if (c0.mid) bulk_g2s(stage + a.off_xl, c0.src, c0.mid, &full[ring.st]);
+                        if (c1.mid) bulk_g2s(stage + a.off_xr, c1.src, c1.mid, &full[ring.st]);
+                        if (c2.mid) bulk_g2s(stage + a.off_g, c2.src, c2.mid, &full[ring.st]);
+                        if (c3.mid) bulk_g2s(stage + a.off_statraw, c3.src, c3.mid, &full[ring.st]);
+                    }
                 }
-                if (lane == 0) {
-                    mbar_arrive_expect_tx(&full[ring.st], (uint32_t)m.slab_bytes + c0.mid + c1.mid + c2.mid + c3.mid);
-                    bulk_g2s(stage, a.slabs + m.slab_off, (uint32_t)m.slab_bytes, &full[ring.st]);
-                    if (c0.mid) bulk_g2s(stage + a.off_xl, c0.src, c0.mid, &full[ring.st]);
-                    if (c1.mid) bulk_g2s(stage + a.off_xr, c1.src, c1.mid, &full[ring.st]);
-                    if (c2.mid) bulk_g2s(stage + a.off_g, c2.src, c2.mid, &full[ring.st]);
-                    if (c3.mid) bulk_g2s(stage + a.off_statraw, c3.src, c3.mid, &full[ring.st]);
-                    mbar_wait(yempty, yph ^ 1u);  // the single y window: released right after the delta pre-pass
-                }
-                __syncwarp();
-                if (c4.tail) {
-                    win_copy_tail(c4, smem + a.off_y, lane);
+                if (do_y) {
+                    const WinCopy c4 = win_copy(a.y, row0, win, RB_F, a.per_f, Rtot);
+                    if (lane == 0) mbar_wait(yempty, yph ^ 1u);  // the single y window: released right after the delta pre-pass
                     __syncwarp();
-                }
-                if (lane == 0) {
-                    mbar_arrive_expect_tx(yfull, c4.mid);
-                    if (c4.mid) bulk_g2s(smem + a.off_y, c4.src, c4.mid, yfull);
+                    if (c4.tail) {
+                        win_copy_tail(c4, smem + a.off_y, lane);
+                        __syncwarp();
+                    }
+                    if (lane == 0) {
+                        mbar_arrive_expect_tx(yfull, c4.mid);
+                        if (c4.mid) bulk_g2s(smem + a.off_y, c4.src, c4.mid, yfull);
+                    }
                 }
                 }
                 ring.advance(NS);
@@ -305,6 +320,7 @@ __global__ void __launch_bounds__(256, 1) edge_bwd_kernel(const EdgeBwdArgs a) {
     }
 
     // ================================ consumer warps ================================
+    if (WG) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kWgConsumerRegs));
     const int npw = HT > 0 ? 32 / pad_heads(HT) : a.npw;
     const int nw = lane & (npw - 1);
     const int h = lane / npw;
@@ -676,13 +692,25 @@ static int launch_bwd(EdgeBwdArgs a, const tecgat_plan_t *plan, int grid, cudaSt
         const tg_tile_meta &m = tl.h_meta[t];
         all_staged = m.eligible && std::max(m.hi - m.lo, 0) <= a.cap_rows && (m.kin_kout & 0xFFFF) <= a.cap_kin && (m.kin_kout >> 16) <= a.cap_kout;
     }
+    const bool wg = ncw == 8;  // 8 consumer warps: only as the warpgroup-split kernels (specialised shapes)
     auto go = [&](auto kern) -> int {
         TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<(unsigned)grid, (ncw + 1) * 32, smem, st>>>(a);
+        kern<<<(unsigned)grid, wg ? 384 : (ncw + 1) * 32, smem, st>>>(a);
         return TECGAT_OK;
     };
     int rc;
-    if (a.semi) rc = go(edge_bwd_kernel<C, ST, VEC, HT, true, true, true>);
+    if (wg) {
+        rc = TECGAT_ENOSUP;
+        if constexpr (HT > 0) {
+            if (a.semi) rc = go(edge_bwd_kernel<C, ST, VEC, HT, true, true, true, true>);
+            else if (all_staged && a.drop_thr == 0) rc = go(edge_bwd_kernel<C, ST, VEC, HT, false, false, false, true>);
+            else if (all_staged) rc = go(edge_bwd_kernel<C, ST, VEC, HT, false, false, true, true>);
+            else rc = go(edge_bwd_kernel<C, ST, VEC, HT, false, true, true, true>);
+        }
+        if (rc == TECGAT_ENOSUP)
+            tecgat_set_error("edge_bwd: a backward tile of %d nodes x %d heads (8 consumer warps) exists only for the specialised shapes "
+                             "(heads = 2, out_channels 5 or 11); build the plan with tile_nodes_bwd = %d", T, H, 7 * a.npw);
+    } else if (a.semi) rc = go(edge_bwd_kernel<C, ST, VEC, HT, true, true, true>);
     else if (HT > 0 && all_staged && a.drop_thr == 0) rc = go(edge_bwd_kernel<C, ST, VEC, HT, false, HT == 0, HT == 0>);  // inference: no hash either
     else if (HT > 0 && all_staged) rc = go(edge_bwd_kernel<C, ST, VEC, HT, false, HT == 0, true>);  // compact: no gather code
     else rc = go(edge_bwd_kernel<C, ST, VEC, HT, false, true, true>);
@@ -714,9 +742,9 @@ extern "C" int tecgat_edge_bwd(const tecgat_plan_t *plan, const void *xl, const 
     TG_REQUIRE(dtype == TECGAT_F32 || dtype == TECGAT_BF16, TECGAT_EINVAL, "edge_bwd: bad dtype %d", dtype);
     const int hp = pad_heads(heads);
     const tg_tiling &tl = plan->bwd;
-    TG_REQUIRE(tl.T % (32 / hp) == 0 && tl.T * hp <= 224, TECGAT_ENOSUP,
-               "edge_bwd: backward tile of %d nodes x %d heads does not map onto <= 7 consumer warps; build the plan with "
-               "tile_nodes_bwd = a multiple of %d and <= %d", tl.T, heads, 32 / hp, 224 / hp);
+    TG_REQUIRE(tl.T % (32 / hp) == 0 && tl.T * hp <= 256, TECGAT_ENOSUP,
+               "edge_bwd: backward tile of %d nodes x %d heads does not map onto <= 8 consumer warps; build the plan with "
+               "tile_nodes_bwd = a multiple of %d and <= %d", tl.T, heads, 32 / hp, 256 / hp);
     const int HC = heads * out_channels;
     TG_REQUIRE(2 * HC <= tl.T * hp, TECGAT_ENOSUP, "edge_bwd: 2*heads*out_channels (%d) exceeds the consumer threads (%d)", 2 * HC, tl.T * hp);
     const bool vec = (HC % 2) == 0;

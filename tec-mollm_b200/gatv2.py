@@ -33,17 +33,20 @@ def _stream(device: torch.device):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
-def tile_nodes_for(heads: int, backward: bool = False) -> int:
+def tile_nodes_for(heads: int, backward: bool = False, out_channels: Optional[int] = None) -> int:
     """Destination nodes per tile of the persistent edge kernels: one lane per (node, head), heads padded to a power
-    of two.  CTA = consumer warps + one producer warp, sized to a multiple of 128 threads (the register-file
-    allocation granule): 15 consumer warps forward (512 threads), 7 backward (256 threads: shared-memory bound)."""
+    of two.  Forward: 15 consumer warps + one producer warp (512 threads, 128 registers).  Backward: 7 consumer warps + one
+    producer warp (256 threads, 253 registers), or -- for the shapes compiled with a fixed head count (heads = 2,
+    out_channels 5 or 11) -- 8 consumer warps + a producer warpgroup that hands its registers over (384 threads,
+    ``setmaxnreg`` 240 / 24)."""
     if heads < 1 or heads > 32:
         raise ValueError(f"heads={heads} unsupported (1..32)")
     hp = 1
     while hp < heads:
         hp *= 2
     npw = 32 // hp  # nodes per warp
-    warps = 7 if backward else 15
+    wide = backward and heads == 2 and out_channels in (5, 11)
+    warps = (8 if wide else 7) if backward else 15
     knob = os.environ.get("TECGAT_TILE_BWD" if backward else "TECGAT_TILE_FWD")  # tuning knob (benchmarks only)
     t = int(knob) if knob else warps * npw
     return max(npw, min(warps * npw, (t // npw) * npw))
@@ -263,7 +266,7 @@ class GATv2Conv(nn.Module):
         self.bias = nn.Parameter(torch.empty(heads * out_channels))
         self._plans = {}
         self._tile_nodes = tile_nodes_for(heads)
-        self._tile_nodes_bwd = tile_nodes_for(heads, backward=True)
+        self._tile_nodes_bwd = tile_nodes_for(heads, backward=True, out_channels=out_channels)
         self.reset_parameters()
 
     def __getstate__(self):  # graph plans hold device handles: never pickled / deep-copied
