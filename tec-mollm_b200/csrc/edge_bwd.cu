@@ -139,9 +139,12 @@ __device__ __forceinline__ void bwd_lane(const CV<C> &attp, const CV<C> &attm, c
     }
     // ---- role 1: v as DESTINATION, in-edges (u -> v): A_in, B_in ------------------------------------------------
     uint32_t hk = (slot0 + 1u) * kDropMul + drop.key;
+    // neighbour indices are fetched one iteration ahead (index load -> address -> row load is the loop's longest dependent
+    // chain); the look-ahead slots past the row's padded length are never used
+    ptrdiff_t ua = nbr_in(1), ub = nbr_in(2);
 #pragma unroll 1
     for (int k = 1; k < kmax_in; k += 2, hk += 2u * kDropMul) {
-        const ptrdiff_t ua = nbr_in(k), ub = nbr_in(k + 1);
+        const ptrdiff_t na = nbr_in(k + 2), nb = nbr_in(k + 3);
         CV<C> xa, xb, sa, sb;
         cv_load<C, VEC>(xa, xl_base + ua * HC, par);
         cv_load<C, VEC>(xb, xl_base + ub * HC, par);
@@ -155,13 +158,19 @@ __device__ __forceinline__ void bwd_lane(const CV<C> &attp, const CV<C> &attm, c
         A_in += da + db;
         acc_step<C>(B_in, sa, da);
         acc_step<C>(B_in, sb, db);
+        ua = na;
+        ub = nb;
     }
     // ---- role 2: v as SOURCE, out-edges (v -> u): A_out, B_out, G = sum alpha q g_u ------------------------------
     wait_ds();  // the (delta, stat) of every window row has been written (other warps' pre-pass shares)
     const float c1 = cv_dot<C>(attp, xl_v);
+    ua = nbr_out(1);
+    ub = nbr_out(2);
+    uint32_t sla = slot_out(1), slb = slot_out(2);
 #pragma unroll 1
     for (int k = 1; k < kmax_out; k += 2) {
-        const ptrdiff_t ua = nbr_out(k), ub = nbr_out(k + 1);
+        const ptrdiff_t na = nbr_out(k + 2), nb = nbr_out(k + 3);
+        const uint32_t nsa = slot_out(k + 2), nsb = slot_out(k + 3);
         CV<C> ra, rb, ga, gb, sa, sb;
         cv_load<C, VEC>(ra, xr_base + ua * HC, par);
         cv_load<C, VEC>(rb, xr_base + ub * HC, par);
@@ -173,13 +182,15 @@ __device__ __forceinline__ void bwd_lane(const CV<C> &attp, const CV<C> &attm, c
         const float gxa = cv_dot<C>(ga, xl_v), gxb = cv_dot<C>(gb, xl_v);
         const float va = k < deg_out ? 1.f : 0.f, vb = k + 1 < deg_out ? 1.f : 0.f;
         const float aa = va * fast_exp2(fminf(ea - dua.y, 100.f)), ab = vb * fast_exp2(fminf(eb - dub.y, 100.f));
-        const float qa = drop.q(slot_out(k)), qb = drop.q(slot_out(k + 1));
+        const float qa = drop.q(sla), qb = drop.q(slb);
         const float da = aa * fmaf(qa, gxa, -dua.x), db = ab * fmaf(qb, gxb, -dub.x);
         A_out += da + db;
         acc_step<C>(B_out, sa, da);
         acc_step<C>(B_out, sb, db);
         cv_axpy<C>(G, aa * qa, ga);
         cv_axpy<C>(G, ab * qb, gb);
+        ua = na; ub = nb;
+        sla = nsa; slb = nsb;
     }
     // ---- rows:  DR = slope A_in + (1-slope) B_in,  d xr = att DR;   DL likewise,  d xl = G + att DL;
     //      d att partial of this row = xr_v DR + xl_v DL   (lrelu(s) = s lrelu'(s), s = xl + xr) ---------------------

@@ -38,7 +38,7 @@ def tile_nodes_for(heads: int, backward: bool = False, out_channels: Optional[in
     of two.  Forward: 15 consumer warps + one producer warp (512 threads, 128 registers).  Backward: 7 consumer warps + one
     producer warp (256 threads, 253 registers), or -- for the shapes compiled with a fixed head count (heads = 2,
     out_channels 5 or 11) -- 8 consumer warps + a producer warpgroup that hands its registers over (384 threads,
-    ``setmaxnreg`` 240 / 24)."""
+    ``setmaxnreg`` 232 / 40)."""
     if heads < 1 or heads > 32:
         raise ValueError(f"heads={heads} unsupported (1..32)")
     hp = 1
