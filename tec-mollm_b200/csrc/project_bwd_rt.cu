@@ -65,7 +65,11 @@ __host__ __device__ inline Smem layout(int F, int HC) {
     s.off_dr = tile_d;
     s.off_x = 2 * tile_d;
     s.stage_bytes = 2 * tile_d + tile_x;
-    s.stage0 = o; o += kStages * s.stage_bytes;
+    s.stage0 = o;
+    {   // the ring doubles as the end-of-kernel scratch: one fp32 partial block [2*HP][kFP] per (team, slice)
+        const uint32_t ring = kStages * s.stage_bytes, scratch = kTeams * Cfg<HP>::kSlices * 2u * kHP * kFP * 4u;
+        o += ring > scratch ? ring : scratch;
+    }
     s.dxst_bytes = ((kRows * F * 4u + 127) / 128) * 128;
     s.dxst = o; o += kTeams * s.dxst_bytes;
     s.total = o;
@@ -147,7 +151,9 @@ __global__ void __launch_bounds__(kThreads, 1) project_bwd_rt_kernel(const Args 
     // ================================ consumer teams ================================
     const int team = warp / kTeamWarps, tw = warp % kTeamWarps;
     const int HCe = (HC + 1) & ~1;
-    double *red = reinterpret_cast<double *>(smem + L.stage0);  // end of kernel: [2*kHP][kFP] fp64 sums (the ring is free by then)
+    // end of kernel (the ring is free by then): [kTeams * kSlices][2*kHP][kFP] fp32 register partials, one block per (team, slice)
+    float *scratch = reinterpret_cast<float *>(smem + L.stage0);
+    constexpr int kBlock = 2 * kHP * kFP;
 
     if (tw < 2) {
         // -------- dx warps: thread = rows {lane, lane+32, lane+64, lane+96} x outputs 12u .. 12u+11 ------------------------
@@ -223,8 +229,7 @@ __global__ void __launch_bounds__(kThreads, 1) project_bwd_rt_kernel(const Args 
         }
         if (need_dx && tw == 0 && lane == 0) bulk_wait0();
         named_bar(8, kConsumers);  // all tiles consumed: the ring is free
-        for (int i = tid; i < 2 * kHP * kFP; i += kConsumers) red[i] = 0.0;
-        for (int g = 0; g <= kTeams * kSlices; ++g) named_bar(8, kConsumers);
+        named_bar(8, kConsumers);  // the dW warps have written their partial blocks
     } else {
         // -------- dW warps: thread = (16-row slice, gradient columns 8 ot .. 8 ot+7, input columns 12 u .. 12 u+11) -------------
         const int q = (tw - 2) * 32 + lane;  // 0 .. 95
@@ -266,23 +271,19 @@ __global__ void __launch_bounds__(kThreads, 1) project_bwd_rt_kernel(const Args 
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
         }
-        // ---- CTA partial: the 24 (team, slice) register partials summed in fp64, fixed order ----------------------------
-        named_bar(8, kConsumers);
-        for (int i = tid; i < 2 * kHP * kFP; i += kConsumers) red[i] = 0.0;
-        named_bar(8, kConsumers);
-        for (int g = 0; g < kTeams * kSlices; ++g) {
-            if (team * kSlices + slice == g) {
+        // ---- CTA partial: every (team, slice) stores its register partials as one fp32 block; after ONE barrier each output is
+        //      summed over the 24 blocks in fp64 in a fixed order (formerly 24 barrier-separated read-modify-write rounds in
+        //      shared memory: ~45 us per launch, half of the kernel at B = 2) ------------------------------------------------
+        named_bar(8, kConsumers);  // all tiles consumed: the ring is free
+        {
+            float *blk = scratch + (team * kSlices + slice) * kBlock;
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < 8; ++i)
 #pragma unroll
-                    for (int k = 0; k < 6; ++k) {
-                        double *p = red + (8 * ot + i) * kFP + 12 * u + 2 * k;
-                        p[0] += (double)acc[i][k].x;
-                        p[1] += (double)acc[i][k].y;
-                    }
-            }
-            named_bar(8, kConsumers);
+                for (int k = 0; k < 6; ++k)
+                    *reinterpret_cast<float2 *>(blk + (8 * ot + i) * kFP + 12 * u + 2 * k) = acc[i][k];
         }
+        named_bar(8, kConsumers);
     }
     const int O = 2 * HC;
     float *out = a.partials + (int64_t)blockIdx.x * (O * F + O);
@@ -290,7 +291,11 @@ __global__ void __launch_bounds__(kThreads, 1) project_bwd_rt_kernel(const Args 
         int o, f;
         if (i < O * F) { o = i / F; f = i - o * F; } else { o = i - O * F; f = kFP - 1; }
         const int arr = o >= HC, c = o - arr * HC;
-        out[i] = (float)red[(arr * kHP + c) * kFP + f];
+        const float *src = scratch + (arr * kHP + c) * kFP + f;
+        double v = 0.0;
+#pragma unroll 4
+        for (int g = 0; g < kTeams * kSlices; ++g) v += (double)src[g * kBlock];
+        out[i] = (float)v;
     }
 }
 

@@ -42,3 +42,26 @@ for B in (2, 8):
     for _ in range(n): g.replay()
     e1.record(); torch.cuda.synchronize()
     print(f"B={B}: eager host-issue {host*1e6:.0f} us/step, eager wall {wall*1e6:.0f} us/step, CUDA-graph replay {e0.elapsed_time(e1)/n*1e3:.0f} us/step")
+
+# where the eager host time goes (B = 2): cProfile of 300 steps, top entries by cumulative time
+if os.environ.get("PROBE_PROFILE", "1") == "1":
+    import cProfile, pstats, io
+    B = 2
+    S, N, F, H, C = B * 48, 2911, 22, 2, 11
+    enc = SpatialEncoder(F, C, heads=H, dropout=0.1).to(dev).train()
+    x = torch.randn(S, N, F, device=dev).requires_grad_(True)
+    gy = torch.randn(S, N, H * C, device=dev)
+    def step2():
+        x.grad = None
+        enc.zero_grad(set_to_none=True)
+        enc(x, ei).backward(gy)
+    for _ in range(20): step2()
+    torch.cuda.synchronize()
+    pr = cProfile.Profile()
+    pr.enable()
+    for _ in range(300): step2()
+    pr.disable()
+    torch.cuda.synchronize()
+    sio = io.StringIO()
+    pstats.Stats(pr, stream=sio).sort_stats("cumulative").print_stats(28)
+    print(sio.getvalue())
