@@ -27,7 +27,17 @@ namespace tg {
 namespace rt {
 constexpr int kRows = 128;   // rows per tile
 constexpr int kFP = 24;      // padded input channels (F <= 22: column 23 carries the constant 1)
-constexpr int kTeams = 3, kTeamWarps = 5;
+#ifndef TG_PBWD_DXW
+#define TG_PBWD_DXW 2
+#endif
+// team = kDxWarps "dx" warps (each 24 / kDxWarps outputs of all 128 rows) + 3 "dW" warps.  Per tile a dx thread issues
+// 4 rows x (kDxOut / 2) x HC FFMA2 and a dW thread 16 rows x 48: with 2 dx warps the dx side is 1.4x the dW side and the dW
+// warps wait on the ring's full barrier (18 % of the samples).  Measured alternative (-DTG_PBWD_DXW=3: two teams of 3 dx
+// warps x 8 outputs + 3 dW warps, balanced 704 vs 768 FFMA2, 12 consumer warps): 1.67 ms against 1.63 ms for the default
+// three teams of 2 + 3 (15 consumer warps) at B = 128 -- the extra warps hide more latency than the balance recovers.
+constexpr int kDxWarps = TG_PBWD_DXW, kDwWarps = 3;
+constexpr int kTeams = kDxWarps == 2 ? 3 : 2, kTeamWarps = kDxWarps + kDwWarps;
+constexpr int kDxOut = 24 / kDxWarps, kDxPairs = kDxOut / 2, kDxVec = kDxOut / 4;
 constexpr int kConsumers = kTeams * kTeamWarps * 32;
 constexpr int kThreads = kConsumers + 32;
 constexpr int kPad = 128;    // zeroed bytes after every staged tile (threads read up to 2 elements past a row)
@@ -155,7 +165,7 @@ __global__ void __launch_bounds__(kThreads, 1) project_bwd_rt_kernel(const Args 
     float *scratch = reinterpret_cast<float *>(smem + L.stage0);
     constexpr int kBlock = 2 * kHP * kFP;
 
-    if (tw < 2) {
+    if (tw < kDxWarps) {
         // -------- dx warps: thread = rows {lane, lane+32, lane+64, lane+96} x outputs 12u .. 12u+11 ------------------------
         const int u = tw;
         float *dxst = reinterpret_cast<float *>(smem + L.dxst + (size_t)team * L.dxst_bytes);
@@ -170,23 +180,23 @@ __global__ void __launch_bounds__(kThreads, 1) project_bwd_rt_kernel(const Args 
                 if (lane == 0) mbar_arrive(&empty[s]);
                 continue;
             }
-            float2 o[4][6];
+            float2 o[4][kDxPairs];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int k = 0; k < 6; ++k) o[i][k] = make_float2(0.f, 0.f);
+                for (int k = 0; k < kDxPairs; ++k) o[i][k] = make_float2(0.f, 0.f);
 #pragma unroll 1
             for (int arr = 0; arr < 2; ++arr) {
                 const ST *d = reinterpret_cast<const ST *>(st + (arr ? L.off_dr : 0u)) + lane * HC;
-                const float *w = W_s + arr * kHP * kFP + 12 * u;
+                const float *w = W_s + arr * kHP * kFP + kDxOut * u;
 #pragma unroll 2
                 for (int c = 0; c < HCe; c += 2) {
                     float2 dv[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) dv[i] = ld_pair(d + 32 * i * HC + c);
-                    float4 w0[3], w1[3];
+                    float4 w0[kDxVec], w1[kDxVec];
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) {
+                    for (int k = 0; k < kDxVec; ++k) {
                         w0[k] = *reinterpret_cast<const float4 *>(w + c * kFP + 4 * k);
                         w1[k] = *reinterpret_cast<const float4 *>(w + (c + 1) * kFP + 4 * k);
                     }
@@ -194,7 +204,7 @@ __global__ void __launch_bounds__(kThreads, 1) project_bwd_rt_kernel(const Args 
                     for (int i = 0; i < 4; ++i) {
                         const float2 a0 = make_float2(dv[i].x, dv[i].x), a1 = make_float2(dv[i].y, dv[i].y);
 #pragma unroll
-                        for (int k = 0; k < 3; ++k) {
+                        for (int k = 0; k < kDxVec; ++k) {
                             o[i][2 * k] = __ffma2_rn(a0, make_float2(w0[k].x, w0[k].y), o[i][2 * k]);
                             o[i][2 * k + 1] = __ffma2_rn(a0, make_float2(w0[k].z, w0[k].w), o[i][2 * k + 1]);
                             o[i][2 * k] = __ffma2_rn(a1, make_float2(w1[k].x, w1[k].y), o[i][2 * k]);
@@ -206,16 +216,16 @@ __global__ void __launch_bounds__(kThreads, 1) project_bwd_rt_kernel(const Args 
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
             if (tw == 0 && lane == 0) bulk_wait_read0();  // the previous tile's bulk store has drained dxst
-            named_bar(1 + team, 64);
+            named_bar(1 + team, kDxWarps * 32);
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int k = 0; k < 6; ++k) {
-                    const int f = 12 * u + 2 * k;
+                for (int k = 0; k < kDxPairs; ++k) {
+                    const int f = kDxOut * u + 2 * k;
                     if (f < F) *reinterpret_cast<float2 *>(dxst + (lane + 32 * i) * F + f) = o[i][k];
                 }
             fence_proxy_async();
-            named_bar(1 + team, 64);
+            named_bar(1 + team, kDxWarps * 32);
             float *gdx = a.dx + r0 * F;
             if (nr == kRows) {
                 if (tw == 0 && lane == 0) {
@@ -224,7 +234,7 @@ __global__ void __launch_bounds__(kThreads, 1) project_bwd_rt_kernel(const Args 
                     bulk_commit();
                 }
             } else {
-                for (int i = tw * 32 + lane; i < nr * F; i += 64) gdx[i] = a.accumulate ? gdx[i] + dxst[i] : dxst[i];
+                for (int i = tw * 32 + lane; i < nr * F; i += kDxWarps * 32) gdx[i] = a.accumulate ? gdx[i] + dxst[i] : dxst[i];
             }
         }
         if (need_dx && tw == 0 && lane == 0) bulk_wait0();
@@ -232,7 +242,7 @@ __global__ void __launch_bounds__(kThreads, 1) project_bwd_rt_kernel(const Args 
         named_bar(8, kConsumers);  // the dW warps have written their partial blocks
     } else {
         // -------- dW warps: thread = (16-row slice, gradient columns 8 ot .. 8 ot+7, input columns 12 u .. 12 u+11) -------------
-        const int q = (tw - 2) * 32 + lane;  // 0 .. 95
+        const int q = (tw - kDxWarps) * 32 + lane;  // 0 .. 95
         const int slice = q / (2 * kOT), ot = (q % (2 * kOT)) >> 1, u = q & 1;
         float2 acc[8][6];
 #pragma unroll
