@@ -21,6 +21,7 @@ of the encoder over the rank's batch; edge-msgs/s = snapshots * E / time with E 
 from __future__ import annotations
 
 import argparse
+import contextlib
 import json
 import os
 import sys
@@ -169,6 +170,31 @@ def workload_config(args, batch_override=None, note=None):
     return cfg
 
 
+@contextlib.contextmanager
+def gpu_local_cpus(gpu_index):
+    """Temporarily bind the calling thread to the CPUs NVML reports as local to GPU ``gpu_index`` so that host buffers
+    allocated inside land on that GPU's NUMA node (at 8 GPUs the H2D copies otherwise cross the socket link).  Yields whether
+    the binding happened; the previous affinity is restored on exit (the CPU baseline leg uses every core)."""
+    old, bound = None, False
+    try:
+        import pynvml
+
+        old = os.sched_getaffinity(0)
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(gpu_index))
+        bound = True
+    except Exception:
+        bound = False
+    try:
+        yield bound
+    finally:
+        if old is not None:
+            try:
+                os.sched_setaffinity(0, old)
+            except Exception:
+                pass
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------------------------
@@ -241,7 +267,8 @@ def run_gpu_arm(args):
     phase_ms = {k: v / args.steps for k, v in phase_ms.items()}
 
     # ---- e2e: x from pinned host memory every step (double-buffered), gradients read back ----------------------
-    x_host = [torch.randn(S, N_NODES, F_IN).pin_memory() for _ in range(2)]
+    with gpu_local_cpus(local_rank) as numa_bound:  # pinned pages land on the GPU's own NUMA node (first touch)
+        x_host = [torch.randn(S, N_NODES, F_IN).pin_memory() for _ in range(2)]
     x_dev = [torch.empty(S, N_NODES, F_IN, device=dev).requires_grad_(True) for _ in range(2)]
     g_host = torch.empty(flat.flat.numel()).pin_memory()
     copy_stream = torch.cuda.Stream(dev)
@@ -312,7 +339,8 @@ def run_gpu_arm(args):
             "phases": phases,
             "whole_path_frac_of_roofline": (rows * sum(bpr.values()) / (step_ms * 1e-3) / 1e9) / peak,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
-                    "h2d_bytes_per_step": world * x_host[0].numel() * 4, "d2h_bytes_per_step": world * g_host.numel() * 4},
+                    "h2d_bytes_per_step": world * x_host[0].numel() * 4, "d2h_bytes_per_step": world * g_host.numel() * 4,
+                    "host_buffers_numa_local": bool(numa_bound)},
             "gpu_launches": 6 * args.steps,
             "clocks": clocks,
         }
