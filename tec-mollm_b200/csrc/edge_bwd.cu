@@ -229,7 +229,10 @@ __global__ void __launch_bounds__(WG ? 384 : 256, 1) edge_bwd_kernel(const EdgeB
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ncw = WG ? 8 : (blockDim.x >> 5) - 1;
     const int nct = ncw * 32;  // consumer threads
-    const int H = HT > 0 ? HT : a.H, HC = H * C, T = a.T, N = a.N;
+    // WG kernels exist only for 8 consumer warps x (32 / heads) nodes: the tile size is a compile-time constant there (the ELL
+    // strides and the row-to-lane map of the delta pre-pass fold into immediates)
+    const int T = (WG && HT > 0) ? 8 * (32 / pad_heads(HT > 0 ? HT : 1)) : a.T;
+    const int H = HT > 0 ? HT : a.H, HC = H * C, N = a.N;
     const int Ts = (T + 7) & ~7;  // row stride of the slab sections
     const int NS = a.num_stages;
     const uint32_t RB_ST = (uint32_t)HC * sizeof(ST), RB_F = (uint32_t)HC * 4u, RB_STAT = (uint32_t)H * 4u;
@@ -435,10 +438,17 @@ __global__ void __launch_bounds__(WG ? 384 : 256, 1) edge_bwd_kernel(const EdgeB
                     if (CV<C>::ODD) dl = fmaf(gg.s, yy.s - bias_h.s, dl);
                     return make_float2(dl, stat_s[r * H + hh]);
                 };
+                // A lane's share of the window starts at its OWN row's residue mod T, so the own row (DESTINATION role: no
+                // waiting on other warps) is one of the rows it computes anyway.
                 const int vl = n0 + node_l - lo;  // own row inside the window
-                const float2 dv = active ? delta_of(vl) : make_float2(0.f, 0.f);
+                float2 dv = make_float2(0.f, 0.f);
                 if (head_ok)
-                    for (int r = node_l; r < win; r += T) ds[hh * a.cap_rows + r] = delta_of(r);
+                    for (int r = vl % T; r < win; r += T) {
+                        const float2 d = delta_of(r);
+                        ds[hh * a.cap_rows + r] = d;
+                        if (r == vl) dv = d;
+                    }
+                if (!active) dv = make_float2(0.f, 0.f);
                 __syncwarp();
                 if (lane == 0) {
                     if (!kSemi) mbar_arrive(yempty);  // y window may be refilled for the next item
