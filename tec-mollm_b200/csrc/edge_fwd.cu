@@ -41,7 +41,7 @@ struct EdgeFwdArgs {
 // slots are walked TWO per iteration, branch-free (slots past the lane's degree read a valid row and get weight 0), so
 // the two edges' instruction streams interleave.
 template <int C, typename ST, bool VEC, bool FAST, bool DROP>
-__device__ __forceinline__ void fwd_lane(const EdgeFwdArgs &a, const CV<C> &attp, const CV<C> &attm, const float *bias_ptr,
+__device__ __forceinline__ void fwd_lane(const int Ts /* slab row stride */, const EdgeFwdArgs &a, const CV<C> &attp, const CV<C> &attm, const float *bias_ptr,
                                          const ST *xr_chunk, const ST *xl_self /* own row, + h*C */,
                                          const ST *xl_lane /* window row 0 (FAST) or snapshot row 0, + h*C */, int HC, int par,
                                          const uint16_t *ell /* + node_l */, const int32_t *col /* + k0 */, int deg, int kmax_w,
@@ -61,7 +61,6 @@ __device__ __forceinline__ void fwd_lane(const EdgeFwdArgs &a, const CV<C> &attp
         shift = edge_score<C>(attp, attm, xl_i, xr_i, s);
     }
     const float e_self = shift;
-    const int Ts = (a.T + 7) & ~7;
     auto nbr = [&](int k) -> int {
         if (FAST) return (int)ell[k * Ts];
         return k < deg ? __ldg(col + k) : 0;
@@ -127,15 +126,16 @@ __device__ __forceinline__ void fwd_lane(const EdgeFwdArgs &a, const CV<C> &attp
 
 // HT > 0: compile-time number of heads (address arithmetic folds); 0: runtime
 // GATHER: the launch contains tiles that are not staged (false drops the gather-from-global code: every item is staged).
-template <int C, typename ST, bool VEC, int HT, bool GATHER, bool DROP>
+// TT > 0: compile-time tile size (nodes) -- the default 15 consumer warps x 32 / heads: the slab strides become immediates
+template <int C, typename ST, bool VEC, int HT, bool GATHER, bool DROP, int TT = 0>
 __global__ void __launch_bounds__(512, 1) edge_fwd_kernel(const EdgeFwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem);
     uint64_t *empty = full + kMaxStages;
     const tg_tile_meta *meta_s = reinterpret_cast<const tg_tile_meta *>(smem + a.off_meta);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ncw = (blockDim.x >> 5) - 1;  // consumer warps; the last warp is the producer
-    const int H = HT > 0 ? HT : a.H, HC = H * C, T = a.T, N = a.N;
+    const int ncw = TT > 0 ? 15 : (blockDim.x >> 5) - 1;  // consumer warps; the last warp is the producer
+    const int H = HT > 0 ? HT : a.H, HC = H * C, T = TT > 0 ? TT : a.T, N = a.N;
     const int Ts = (T + 7) & ~7;  // row stride of the slab sections
     const int NS = a.num_stages;
     constexpr uint32_t ES = sizeof(ST);
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(512, 1) edge_fwd_kernel(const EdgeFwdArgs a) {
             if (lit) deg = min(deg, 1);
             const uint32_t slot0 = active ? (uint32_t)k0s[node_l] : 0u;
             const int kmax_w = __reduce_max_sync(0xFFFFFFFFu, deg);
-            fwd_lane<C, ST, VEC, true, DROP>(a, attp, attm, bias_h, xr_s + node_l * HC + hh * C, xl_s + (n0 + node_l - lo) * HC + hh * C,
+            fwd_lane<C, ST, VEC, true, DROP>(Ts, a, attp, attm, bias_h, xr_s + node_l * HC + hh * C, xl_s + (n0 + node_l - lo) * HC + hh * C,
                                        xl_s + hh * C, HC, par, ell, nullptr, deg, kmax_w, slot0, key, out, stat);
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[ring.st]);  // this warp no longer reads the stage
@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(512, 1) edge_fwd_kernel(const EdgeFwdArgs a) {
             const int kmax_w = __reduce_max_sync(0xFFFFFFFFu, deg);
             const ST *xl_snap = static_cast<const ST *>(a.xl) + (int64_t)snap * N * HC + hh * C;
             const ST *xr_chunk = static_cast<const ST *>(a.xr) + row * HC + hh * C;
-            fwd_lane<C, ST, VEC, false, DROP>(a, attp, attm, bias_h, xr_chunk, xl_snap + (int64_t)(n0 + node_l) * HC, xl_snap, HC, par, nullptr,
+            fwd_lane<C, ST, VEC, false, DROP>(Ts, a, attp, attm, bias_h, xr_chunk, xl_snap + (int64_t)(n0 + node_l) * HC, xl_snap, HC, par, nullptr,
                                         a.col + k0, deg, kmax_w, (uint32_t)k0, key, out, stat);
             if (active) cv_store<C, VEC>(a.y + row * HC + hh * C, out, par);
         }
@@ -365,7 +365,10 @@ static int launch_fwd(EdgeFwdArgs a, const tecgat_plan_t *plan, cudaStream_t st)
         return TECGAT_OK;
     };
     int rc;
-    if (HT > 0 && all_staged && a.drop_thr == 0) rc = go(edge_fwd_kernel<C, ST, VEC, HT, HT == 0, HT == 0>);  // inference: no hash either
+    constexpr int kTT = HT > 0 ? 15 * (32 / pad_heads(HT > 0 ? HT : 1)) : 0;  // the default tile of the fixed-head kernels
+    if (HT > 0 && all_staged && T == kTT && a.drop_thr == 0) rc = go(edge_fwd_kernel<C, ST, VEC, HT, HT == 0, HT == 0, kTT>);
+    else if (HT > 0 && all_staged && T == kTT) rc = go(edge_fwd_kernel<C, ST, VEC, HT, HT == 0, true, kTT>);
+    else if (HT > 0 && all_staged && a.drop_thr == 0) rc = go(edge_fwd_kernel<C, ST, VEC, HT, HT == 0, HT == 0>);  // inference: no hash either
     else if (HT > 0 && all_staged) rc = go(edge_fwd_kernel<C, ST, VEC, HT, HT == 0, true>);  // compact: no gather code
     else rc = go(edge_fwd_kernel<C, ST, VEC, HT, true, true>);
     if (rc != TECGAT_OK) return rc;
