@@ -147,6 +147,11 @@ __device__ __forceinline__ float fast_exp2(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+__device__ __forceinline__ float fast_rcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ float fast_log2(float x) {
     float y;
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -186,8 +191,14 @@ struct Ring {
 // tile table: shared memory when it fits (kMetaSmemTiles), global memory (L1 / L2) otherwise
 constexpr int kMetaSmemTiles = 64;
 __device__ __forceinline__ tg_tile_meta load_meta(const tg_tile_meta *smem_tab, const tg_tile_meta *gmem_tab, int num_tiles, int tile) {
-    const tg_tile_meta *src = num_tiles <= kMetaSmemTiles ? smem_tab + tile : gmem_tab + tile;
-    const int4 a = reinterpret_cast<const int4 *>(src)[0], b = reinterpret_cast<const int4 *>(src)[1];
+    int4 a, b;  // two explicit paths: a pointer select would turn both into generic-address loads
+    if (num_tiles <= kMetaSmemTiles) {
+        a = reinterpret_cast<const int4 *>(smem_tab + tile)[0];
+        b = reinterpret_cast<const int4 *>(smem_tab + tile)[1];
+    } else {
+        a = __ldg(reinterpret_cast<const int4 *>(gmem_tab + tile));
+        b = __ldg(reinterpret_cast<const int4 *>(gmem_tab + tile) + 1);
+    }
     tg_tile_meta m;
     m.lo = a.x; m.hi = a.y; m.kin_kout = a.z; m.eligible = a.w;
     m.slab_off = (int64_t)(uint32_t)b.x | ((int64_t)b.y << 32);

@@ -114,7 +114,7 @@ __device__ __forceinline__ void fwd_lane(const int Ts /* slab row stride */, con
         }
         shift = mx;
     }
-    const float inv = l > 0.f ? __frcp_rn(l) : 0.f;
+    const float inv = l > 0.f ? fast_rcp(l) : 0.f;  // MUFU.RCP (1 ulp): the IEEE sequence is a range check + two Newton steps
     const float2 inv2 = splat(inv);
     CV<C> bias_h;  // read here (L1 hit) instead of living in 11 registers through the edge loop
     cv_load_param<C>(bias_h, bias_ptr, par, 1.f);
