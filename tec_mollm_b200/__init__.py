@@ -1,9 +1,9 @@
-"""Import alias: the package lives in ``tec-mollm_b200/`` (a name Python cannot import directly);
-``import tec_mollm_b200`` resolves every submodule there."""
-import os as _os
+"""tec_mollm_b200 -- B200-native (sm_100a) drop-in for TEC-MoLLM's GATv2 SpatialEncoder and its haversine
+graph builder.  Python here is plumbing (tensors, autograd wiring, torch.distributed); every number is
+computed by the hand-written CUDA library ``lib/libtecgat.so`` behind the C ABI in ``include/tecgat.h``."""
+from .gatv2 import GATv2Conv, GraphPlan, tile_nodes_for  # noqa: F401
+from .spatial_encoder import SpatialEncoder  # noqa: F401
+from . import graph  # noqa: F401
+from . import dist  # noqa: F401
 
-_real = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "tec-mollm_b200")
-__path__ = [_real]
-__file__ = _os.path.join(_real, "__init__.py")
-with open(__file__) as _f:
-    exec(compile(_f.read(), __file__, "exec"))
+__all__ = ["GATv2Conv", "GraphPlan", "SpatialEncoder", "graph", "dist", "tile_nodes_for"]

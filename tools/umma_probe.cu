@@ -12,7 +12,7 @@
 #include <vector>
 #include <cmath>
 
-#include "../tec-mollm_b200/csrc/tc.cuh"
+#include "../tec_mollm_b200/csrc/tc.cuh"
 
 using namespace tg;
 
