@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TECGAT_ABI_VERSION 2
+#define TECGAT_ABI_VERSION 3
 
 /* error codes */
 #define TECGAT_OK 0
@@ -116,6 +116,45 @@ int tecgat_edge_bwd(const tecgat_plan_t *plan, const void *xl_dev, const void *x
                     float *datt_dev, float *dbias_dev, void *workspace_dev, int32_t snapshots,
                     int32_t heads, int32_t out_channels, float negative_slope, float dropout_p,
                     uint64_t seed, int32_t mode, int32_t dtype, void *stream);
+
+/* ---- one call per direction: what GATv2Conv.forward (src/model/modules.py:356) and its autograd backward are for the
+ *      reference.  tecgat_forward = tecgat_project_fwd + tecgat_edge_fwd.  tecgat_backward = tecgat_edge_bwd +
+ *      tecgat_project_bwd with ONE fixed-order finish of all six parameter gradients (5 launches per training step in
+ *      total, against ~45 ATen launches in PyG).
+ *        seed_dev      : when non-NULL the dropout seed is read from device memory (see tecgat_seed_advance) and `seed` is
+ *                        ignored -- a captured CUDA graph then draws a fresh mask on every replay;
+ *        dx_accumulate : dx += (dx pre-loaded with the residual branch's gradient, see tecgat_project_bwd_acc);
+ *        grad_accumulate : the six parameter gradients are ADDED to what the buffers hold (the caller's .grad storage:
+ *                        replaces autograd's six accumulation kernels); needs tecgat_backward_fused_supported() == 1.
+ *      workspace: tecgat_backward_workspace() bytes. */
+int tecgat_forward(const tecgat_plan_t *plan, const float *x_dev, const float *wl_dev, const float *bl_dev,
+                   const float *wr_dev, const float *br_dev, const float *att_dev, const float *bias_dev,
+                   void *xl_dev, void *xr_dev, float *y_dev, float *stat_dev, int32_t snapshots,
+                   int32_t in_channels, int32_t heads, int32_t out_channels, float negative_slope,
+                   float dropout_p, uint64_t seed, const uint64_t *seed_dev, int32_t mode, int32_t dtype,
+                   int32_t impl, void *stream);
+int64_t tecgat_backward_workspace(const tecgat_plan_t *plan, int32_t snapshots, int32_t in_channels,
+                                  int32_t heads, int32_t out_channels, int32_t impl);
+int tecgat_backward_fused_supported(int32_t in_channels, int32_t hc, int32_t impl);
+int tecgat_backward(const tecgat_plan_t *plan, const float *x_dev, const float *wl_dev, const float *wr_dev,
+                    const float *att_dev, const float *bias_dev, const void *xl_dev, const void *xr_dev,
+                    const float *y_dev, const float *stat_dev, const float *gy_dev, void *dxl_dev,
+                    void *dxr_dev, float *dx_dev, int32_t dx_accumulate, float *dwl_dev, float *dbl_dev,
+                    float *dwr_dev, float *dbr_dev, float *datt_dev, float *dbias_dev,
+                    int32_t grad_accumulate, void *workspace_dev, int32_t snapshots, int32_t in_channels,
+                    int32_t heads, int32_t out_channels, float negative_slope, float dropout_p, uint64_t seed,
+                    const uint64_t *seed_dev, int32_t mode, int32_t dtype, int32_t impl, void *stream);
+
+/* Device-resident dropout seed (replaces the Philox state torch.nn.functional.dropout advances inside PyG's message
+ * step): state_dev = {seed, counter}; writes a fresh 64-bit seed to *seed_out_dev and bumps the counter, on `stream`. */
+int tecgat_seed_advance(uint64_t *state_dev, uint64_t *seed_out_dev, void *stream);
+
+/* Instrumentation.  tecgat_launch_count: kernels launched by this library since it was loaded.  tecgat_phase_timing(1):
+ * tecgat_forward / tecgat_backward record CUDA events between their phases on the caller's stream; tecgat_phase_times
+ * synchronises them and returns (then clears) the accumulated milliseconds of {proj_fwd, edge_fwd, edge_bwd, proj_bwd}. */
+int64_t tecgat_launch_count(void);
+int tecgat_phase_timing(int32_t enable);
+int tecgat_phase_times(double *ms_out4_host);
 
 /* Host restatement of the kernels' counter-based dropout RNG (pure integer arithmetic), so tests can
  * hand the oracle exactly the mask the kernels used.  Global slot g = snapshot * edges_per_snapshot + CSR slot;

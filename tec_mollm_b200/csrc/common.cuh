@@ -6,6 +6,8 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -34,6 +36,17 @@ void tecgat_set_error(const char *fmt, ...);
     } while (0)
 
 #define TG_LAUNCH_CHECK() TG_CUDA(cudaGetLastError())
+
+// ---- per-launch host overhead, paid once (plan.cu) ------------------------------------------------
+// Number of kernels this library has launched since load (tecgat_launch_count): every `<<<>>>` is followed by
+// tg_count_launch(), so a benchmark can report how many of OUR kernels ran inside its timed region.
+void tg_count_launch(int n = 1);
+// SM count of the current device (queried once per device).
+int tg_sm_count();
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device, size) instead of on every launch.
+cudaError_t tg_set_smem(const void *kernel, int bytes);
+// environment tuning knobs, read once per process (getenv on every launch shows up at B = 2)
+const char *tg_env(const char *name);
 
 // One tiling of the node axis: tiles of T consecutive nodes, each with the contiguous row window [lo, hi) it touches and
 // a "slab" -- the tile's slice of the graph in ELL form, laid out so that ONE bulk-TMA copy brings it into shared memory:
@@ -81,6 +94,12 @@ struct tecgat_plan {
     int32_t *h_col_in = nullptr;
     int32_t *h_eid_in = nullptr;
     int device = 0;
+    // launch geometry of the edge kernels (ring depth, staged caps, shared-memory map): derived once per
+    // (kernel, heads, channels, dtype) from the tilings instead of on every launch; POD blobs keyed by the launcher
+    mutable std::mutex cache_mu;
+    mutable std::map<uint64_t, std::vector<unsigned char>> geom_cache;
+    // sliding-window backward tiling (edge_bwd_sw.cu), built by plan_create when the graph is banded
+    struct tg_sw_plan *sw = nullptr;
 };
 
 // ------------------------------------------------------------------------------------------------

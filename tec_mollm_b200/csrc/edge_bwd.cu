@@ -13,6 +13,7 @@
 // Execution model, lane mapping and arithmetic: edge_common.cuh.
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <type_traits>
 #include <utility>
 #include <vector>
@@ -34,6 +35,7 @@ struct EdgeBwdArgs {
     float slope, inv_keep;
     uint32_t drop_thr;
     uint64_t seed;
+    const uint64_t *seed_dev;  // non-NULL: the seed lives in device memory (the one the forward used)
     int32_t literal;
     int32_t cap_rows, cap_kin, cap_kout, num_stages;
     int32_t semi;  // 1: rows too wide for shared memory -- stage only slab + stat + delta planes, gather the rows from L2
@@ -351,6 +353,7 @@ __global__ void __launch_bounds__(WG ? 384 : 256, 1) edge_bwd_kernel(const EdgeB
     const uint32_t head_key = dropout_head_key((uint32_t)hh);
     uint32_t key = 0;
     int key_snap = -1;
+    const uint64_t seed = (DROP && a.seed_dev) ? __ldg(a.seed_dev) : a.seed;
     // per-lane fp32 partial sums of d att and d bias: one term per item, flushed to a CTA partial row every kFlushItems
     // items (the second stage sums all rows in fp64)
     CV<C> acc_att, acc_bias;
@@ -400,7 +403,7 @@ __global__ void __launch_bounds__(WG ? 384 : 256, 1) edge_bwd_kernel(const EdgeB
         const bool active = head_ok && node_l < nt;
         const int64_t row = (int64_t)snap * N + n0 + node_l;
         if (DROP && a.drop_thr && snap != key_snap) {
-            key = dropout_snapshot_key(a.seed, (uint32_t)snap) ^ head_key;
+            key = dropout_snapshot_key(seed, (uint32_t)snap) ^ head_key;
             key_snap = snap;
         }
         DropCfg<DROP> drop;
@@ -649,10 +652,8 @@ static StagePickBwd pick_stages_bwd(const tg_tiling &tl, const BwdGeom &g, size_
 }
 
 static int bwd_grid(const tecgat_plan_t *plan, int32_t snapshots) {
-    int dev = 0, sms = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int64_t items = int64_t(plan->bwd.num_tiles) * snapshots;
-    return (int)std::min<int64_t>(items, sms);
+    return (int)std::min<int64_t>(items, tg_sm_count());
 }
 
 static int bwd_max_flushes(const tecgat_plan_t *plan, int32_t snapshots) {  // partial rows per CTA
@@ -661,62 +662,95 @@ static int bwd_max_flushes(const tecgat_plan_t *plan, int32_t snapshots) {  // p
     return (int)(((items + g - 1) / g) / kFlushItems + 1);
 }
 
+struct BwdGeomCached {  // everything launch_bwd derives from (tiling, heads, channels, dtype): cached in the plan
+    int32_t npw, semi, num_stages, cap_rows, cap_kin, cap_kout, per_st, per_f, per_stat, all_staged;
+    uint32_t stage_bytes, off_meta, off_red, off_stage0, off_y, off_out, off_statraw, off_ds, off_xl, off_xr, off_g, smem;
+};
+
 template <int C, typename ST, bool VEC, int HT = 0>
 static int launch_bwd(EdgeBwdArgs a, const tecgat_plan_t *plan, int grid, cudaStream_t st) {
     const tg_tiling &tl = plan->bwd;
     const int H = a.H, HC = H * C, T = tl.T;
     const int hp = pad_heads(H);
-    a.npw = 32 / hp;
-    const int ncw = T / a.npw;
-    BwdGeom g{T, H, HC, sizeof(ST), row_period(uint32_t(HC * sizeof(ST))), row_period(uint32_t(HC * 4)), row_period(uint32_t(H * 4))};
-    a.per_st = g.per_st; a.per_f = g.per_f; a.per_stat = g.per_stat;
-    const size_t out_bytes = (2 * size_t(T) * HC * sizeof(ST) + 15) & ~size_t(15);
-    const size_t red_bytes = (size_t(ncw) * H * 2 * C * sizeof(float) + 15) & ~size_t(15);
-    const size_t meta_bytes = tl.num_tiles <= kMetaSmemTiles ? size_t(tl.num_tiles) * 32 : 0;
-    const size_t fixed = 128 + meta_bytes + red_bytes + out_bytes;
-    const char *env = getenv("TECGAT_BWD_STAGES");
+    const char *env = tg_env("TECGAT_BWD_STAGES");
     const int want = env ? std::max(1, std::min(kMaxStages, atoi(env))) : 2;
-    StagePickBwd sp = pick_stages_bwd(tl, g, fixed, want);
-    a.semi = 0;
-    {   // rows too wide for full staging (e.g. H*C = 44 on the 300 km graph): stage slab + stat + delta planes only
-        int full_tiles = 0;
-        for (int t = 0; t < tl.num_tiles; ++t) {
-            const tg_tile_meta &m = tl.h_meta[t];
-            full_tiles += sp.num_stages > 0 && m.eligible && m.hi - m.lo <= sp.cap_rows && (m.kin_kout & 0xFFFF) <= sp.cap_kin &&
-                          (m.kin_kout >> 16) <= sp.cap_kout;
+    const bool force_semi = tg_env("TECGAT_EDGE_SEMI") != nullptr, nostage = tg_env("TECGAT_EDGE_NOSTAGE") != nullptr;  // tests
+    const uint64_t key = (uint64_t(2) << 56) | (uint64_t(C) << 40) | (uint64_t(H) << 32) | (uint64_t(sizeof(ST)) << 24) |
+                         (uint64_t(VEC) << 16) | (uint64_t(want) << 8) | (uint64_t(force_semi) << 1) | uint64_t(nostage);
+    BwdGeomCached c;
+    bool hit = false;
+    {
+        std::lock_guard<std::mutex> lk(plan->cache_mu);
+        auto it = plan->geom_cache.find(key);
+        if (it != plan->geom_cache.end()) {
+            memcpy(&c, it->second.data(), sizeof(c));
+            hit = true;
         }
-        if ((2 * full_tiles < tl.num_tiles || getenv("TECGAT_EDGE_SEMI")) && !getenv("TECGAT_EDGE_NOSTAGE")) {  // TECGAT_EDGE_SEMI: tests
-            const StagePickBwd ss = pick_stages_bwd(tl, g, fixed, want, true);
-            if (ss.num_stages > 0) {
-                sp = ss;
-                a.semi = 1;
+    }
+    if (!hit) {
+        c.npw = 32 / hp;
+        const int ncw0 = T / c.npw;
+        BwdGeom g{T, H, HC, sizeof(ST), row_period(uint32_t(HC * sizeof(ST))), row_period(uint32_t(HC * 4)), row_period(uint32_t(H * 4))};
+        c.per_st = g.per_st; c.per_f = g.per_f; c.per_stat = g.per_stat;
+        const size_t out_bytes = (2 * size_t(T) * HC * sizeof(ST) + 15) & ~size_t(15);
+        const size_t red_bytes = (size_t(ncw0) * H * 2 * C * sizeof(float) + 15) & ~size_t(15);
+        const size_t meta_bytes = tl.num_tiles <= kMetaSmemTiles ? size_t(tl.num_tiles) * 32 : 0;
+        const size_t fixed = 128 + meta_bytes + red_bytes + out_bytes;
+        StagePickBwd sp = pick_stages_bwd(tl, g, fixed, want);
+        c.semi = 0;
+        {   // rows too wide for full staging (e.g. H*C = 44 on the 300 km graph): stage slab + stat + delta planes only
+            int full_tiles = 0;
+            for (int t = 0; t < tl.num_tiles; ++t) {
+                const tg_tile_meta &m = tl.h_meta[t];
+                full_tiles += sp.num_stages > 0 && m.eligible && m.hi - m.lo <= sp.cap_rows && (m.kin_kout & 0xFFFF) <= sp.cap_kin &&
+                              (m.kin_kout >> 16) <= sp.cap_kout;
+            }
+            if ((2 * full_tiles < tl.num_tiles || force_semi) && !nostage) {
+                const StagePickBwd ss = pick_stages_bwd(tl, g, fixed, want, true);
+                if (ss.num_stages > 0) {
+                    sp = ss;
+                    c.semi = 1;
+                }
             }
         }
+        c.num_stages = sp.num_stages > 0 ? sp.num_stages : 1;
+        c.cap_rows = sp.cap_rows;
+        c.cap_kin = sp.num_stages > 0 ? sp.cap_kin : -1;
+        if (nostage) c.cap_kin = -1;  // tests: force the gather-from-global path
+        c.cap_kout = sp.cap_kout;
+        const size_t ybytes = c.semi ? 16 : g.win_f(c.cap_rows);
+        c.off_meta = 128;
+        c.off_red = (uint32_t)(128 + meta_bytes);
+        c.off_y = (uint32_t)(c.off_red + red_bytes);
+        c.off_out = (uint32_t)(c.off_y + ybytes);
+        c.off_stage0 = (uint32_t)((c.off_out + out_bytes + 127) & ~size_t(127));
+        c.stage_bytes = sp.stage_bytes;
+        c.off_statraw = sp.off_statraw; c.off_ds = sp.off_ds; c.off_xl = sp.off_xl; c.off_xr = sp.off_xr; c.off_g = sp.off_g;
+        c.smem = (uint32_t)(c.off_stage0 + size_t(sp.num_stages) * c.stage_bytes);
+        bool all_staged = c.cap_kin >= 0;
+        for (int t = 0; t < tl.num_tiles && all_staged; ++t) {
+            const tg_tile_meta &m = tl.h_meta[t];
+            all_staged = m.eligible && std::max(m.hi - m.lo, 0) <= c.cap_rows && (m.kin_kout & 0xFFFF) <= c.cap_kin && (m.kin_kout >> 16) <= c.cap_kout;
+        }
+        c.all_staged = all_staged;
+        std::lock_guard<std::mutex> lk(plan->cache_mu);
+        auto &blob = plan->geom_cache[key];
+        blob.resize(sizeof(c));
+        memcpy(blob.data(), &c, sizeof(c));
     }
-    a.num_stages = sp.num_stages > 0 ? sp.num_stages : 1;
-    a.cap_rows = sp.cap_rows;
-    a.cap_kin = sp.num_stages > 0 ? sp.cap_kin : -1;
-    if (getenv("TECGAT_EDGE_NOSTAGE")) a.cap_kin = -1;  // tests: force the gather-from-global path
-    a.cap_kout = sp.cap_kout;
-    const size_t ybytes = a.semi ? 16 : g.win_f(a.cap_rows);
-    a.off_meta = 128;
-    a.off_red = (uint32_t)(128 + meta_bytes);
-    a.off_y = (uint32_t)(a.off_red + red_bytes);
-    a.off_out = (uint32_t)(a.off_y + ybytes);
-    a.off_stage0 = (uint32_t)((a.off_out + out_bytes + 127) & ~size_t(127));
-    a.stage_bytes = sp.stage_bytes;
-    a.off_statraw = sp.off_statraw; a.off_ds = sp.off_ds; a.off_xl = sp.off_xl; a.off_xr = sp.off_xr; a.off_g = sp.off_g;
-    const size_t smem = a.off_stage0 + size_t(sp.num_stages) * a.stage_bytes;
+    a.npw = c.npw; a.semi = c.semi; a.num_stages = c.num_stages; a.cap_rows = c.cap_rows; a.cap_kin = c.cap_kin; a.cap_kout = c.cap_kout;
+    a.per_st = c.per_st; a.per_f = c.per_f; a.per_stat = c.per_stat;
+    a.stage_bytes = c.stage_bytes; a.off_meta = c.off_meta; a.off_red = c.off_red; a.off_stage0 = c.off_stage0; a.off_y = c.off_y;
+    a.off_out = c.off_out; a.off_statraw = c.off_statraw; a.off_ds = c.off_ds; a.off_xl = c.off_xl; a.off_xr = c.off_xr; a.off_g = c.off_g;
+    const size_t smem = c.smem;
+    const bool all_staged = c.all_staged != 0;
+    const int ncw = T / a.npw;
     TG_REQUIRE(smem <= 227 * 1024, TECGAT_ENOSUP, "edge_bwd: %zu B shared memory needed (tile %d x %d channels)", smem, T, HC);
-    bool all_staged = a.cap_kin >= 0;
-    for (int t = 0; t < tl.num_tiles && all_staged; ++t) {
-        const tg_tile_meta &m = tl.h_meta[t];
-        all_staged = m.eligible && std::max(m.hi - m.lo, 0) <= a.cap_rows && (m.kin_kout & 0xFFFF) <= a.cap_kin && (m.kin_kout >> 16) <= a.cap_kout;
-    }
     const bool wg = ncw == 8;  // 8 consumer warps: only as the warpgroup-split kernels (specialised shapes)
     auto go = [&](auto kern) -> int {
-        TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TG_CUDA(tg_set_smem(reinterpret_cast<const void *>(kern), (int)smem));
         kern<<<(unsigned)grid, wg ? 384 : (ncw + 1) * 32, smem, st>>>(a);
+        tg_count_launch();
         return TECGAT_OK;
     };
     int rc;
@@ -753,8 +787,17 @@ extern "C" int tecgat_edge_bwd(const tecgat_plan_t *plan, const void *xl, const 
                                void *dxr, float *datt, float *dbias, void *workspace, int32_t snapshots, int32_t heads,
                                int32_t out_channels, float negative_slope, float dropout_p, uint64_t seed, int32_t mode,
                                int32_t dtype, void *stream) {
+    TG_REQUIRE(datt && dbias, TECGAT_EINVAL, "edge_bwd: NULL argument");
+    return tg::edge_bwd_run(plan, xl, xr, att, bias, y, stat, gy, dxl, dxr, datt, dbias, workspace, snapshots, heads, out_channels,
+                            negative_slope, dropout_p, seed, nullptr, mode, dtype, stream, true, nullptr);
+}
+
+int tg::edge_bwd_run(const tecgat_plan_t *plan, const void *xl, const void *xr, const float *att, const float *bias, const float *y,
+                     const float *stat, const float *gy, void *dxl, void *dxr, float *datt, float *dbias, void *workspace,
+                     int32_t snapshots, int32_t heads, int32_t out_channels, float negative_slope, float dropout_p, uint64_t seed,
+                     const uint64_t *seed_dev, int32_t mode, int32_t dtype, void *stream, bool reduce, int64_t *partial_rows) {
     using namespace tg;
-    TG_REQUIRE(plan && xl && xr && att && bias && y && stat && gy && dxl && dxr && datt && dbias && workspace,
+    TG_REQUIRE(plan && xl && xr && att && bias && y && stat && gy && dxl && dxr && workspace,
                TECGAT_EINVAL, "edge_bwd: NULL argument");
     TG_REQUIRE(snapshots > 0 && heads > 0 && out_channels > 0, TECGAT_EINVAL, "edge_bwd: non-positive size");
     TG_REQUIRE(heads <= 32, TECGAT_ENOSUP, "edge_bwd: heads %d > 32", heads);
@@ -785,6 +828,7 @@ extern "C" int tecgat_edge_bwd(const tecgat_plan_t *plan, const void *xl, const 
     a.drop_thr = dropout_p > 0.f ? std::max(1u, dropout_threshold(dropout_p)) : 0u;
     a.inv_keep = 1.f / (1.f - dropout_p);
     a.seed = seed;
+    a.seed_dev = seed_dev;
     a.literal = (mode == TECGAT_MODE_LITERAL);
     a.items = int64_t(tl.num_tiles) * snapshots;
     const int grid = bwd_grid(plan, snapshots);
@@ -808,6 +852,8 @@ extern "C" int tecgat_edge_bwd(const tecgat_plan_t *plan, const void *xl, const 
     }
 #undef TG_CASE
     if (rc != TECGAT_OK) return rc;
+    if (partial_rows) *partial_rows = int64_t(grid) * a.max_flushes;
+    if (!reduce) return TECGAT_OK;
     ReduceSegs segs = {{datt, dbias, nullptr, nullptr}, {0, HC, 0, 0}, {HC, 2 * HC, 0, 0}};
     return reduce_columns(a.partials, int64_t(grid) * a.max_flushes, 2 * HC, segs, st);
 }

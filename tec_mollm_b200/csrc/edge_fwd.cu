@@ -10,6 +10,7 @@
 // Saved for backward: ONE float per (row, head), stat = shift + log2(sum), i.e. alpha_ij = exp2(e_ij - stat).
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <utility>
 #include <vector>
 
@@ -28,6 +29,7 @@ struct EdgeFwdArgs {
     float slope, inv_keep;
     uint32_t drop_thr;
     uint64_t seed;
+    const uint64_t *seed_dev;  // non-NULL: the seed lives in device memory (CUDA-graph replays draw fresh masks)
     int32_t literal;
     int32_t cap_rows, cap_k, num_stages;
     int32_t per;  // 16-byte row period of xl / xr (rows)
@@ -205,6 +207,7 @@ __global__ void __launch_bounds__(512, 1) edge_fwd_kernel(const EdgeFwdArgs a) {
     const uint32_t head_key = dropout_head_key((uint32_t)hh);
     uint32_t key = 0;
     int key_snap = -1;
+    const uint64_t seed = (DROP && a.seed_dev) ? __ldg(a.seed_dev) : a.seed;
 
     for (int w = 0; w < n_items; ++w) {
         const tg_tile_meta m = load_meta(meta_s, a.meta, a.num_tiles, tile);
@@ -215,7 +218,7 @@ __global__ void __launch_bounds__(512, 1) edge_fwd_kernel(const EdgeFwdArgs a) {
         const bool active = head_ok && node_l < nt;
         const int64_t row = (int64_t)snap * N + n0 + node_l;
         if (DROP && a.drop_thr && snap != key_snap) {
-            key = dropout_snapshot_key(a.seed, (uint32_t)snap) ^ head_key;
+            key = dropout_snapshot_key(seed, (uint32_t)snap) ^ head_key;
             key_snap = snap;
         }
         CV<C> out;
@@ -324,44 +327,73 @@ static StagePick pick_stages(const tg_tiling &tl, int T, int HC, size_t es, int 
     return best;
 }
 
+struct FwdGeom {  // everything launch_fwd derives from (tiling, heads, channels, dtype): cached in the plan
+    int32_t npw, per, num_stages, cap_rows, cap_k;
+    uint32_t stage_bytes, off_meta, off_stage0, off_xr, off_xl, off_y;
+    uint32_t smem;
+    int32_t all_staged;
+};
+
 template <int C, typename ST, bool VEC, int HT = 0>
 static int launch_fwd(EdgeFwdArgs a, const tecgat_plan_t *plan, cudaStream_t st) {
     const tg_tiling &tl = plan->fwd;
     const int HC = a.H * C, T = tl.T;
     const int hp = pad_heads(a.H);
-    a.npw = 32 / hp;
-    const int ncw = T / a.npw;  // consumer warps
-    const size_t ybytes = size_t(T) * HC * sizeof(float);
-    a.per = row_period(uint32_t(HC * sizeof(ST)));
-    a.off_meta = 128;
-    a.off_y = 128 + (tl.num_tiles <= kMetaSmemTiles ? tl.num_tiles * 32 : 0);
-    a.off_stage0 = (uint32_t)((a.off_y + ybytes + 127) & ~size_t(127));
-    const char *env = getenv("TECGAT_FWD_STAGES");  // tuning knob: ring depth wanted
+    const char *env = tg_env("TECGAT_FWD_STAGES");  // tuning knob: ring depth wanted
     const int want = env ? std::max(1, std::min(kMaxStages, atoi(env))) : 3;
-    const StagePick sp = pick_stages(tl, T, HC, sizeof(ST), a.per, a.off_stage0, want);
-    a.num_stages = sp.num_stages > 0 ? sp.num_stages : 1;
-    a.cap_rows = sp.cap_rows;
-    a.cap_k = sp.num_stages > 0 ? sp.cap_k : -1;  // -1: nothing is staged
-    if (getenv("TECGAT_EDGE_NOSTAGE")) a.cap_k = -1;  // tests: force the gather-from-global path
-    a.stage_bytes = sp.stage_bytes;
-    a.off_xr = sp.off_xr;
-    a.off_xl = sp.off_xl;
-    const size_t smem = a.off_stage0 + size_t(a.num_stages) * a.stage_bytes;
-    bool all_staged = a.cap_k >= 0;
-    for (int t = 0; t < tl.num_tiles && all_staged; ++t) {
-        const tg_tile_meta &m = tl.h_meta[t];
-        all_staged = m.eligible && m.hi - m.lo <= a.cap_rows && (m.kin_kout & 0xFFFF) <= a.cap_k;
+    const bool nostage = tg_env("TECGAT_EDGE_NOSTAGE") != nullptr;  // tests: force the gather-from-global path
+    const uint64_t key = (uint64_t(1) << 56) | (uint64_t(C) << 40) | (uint64_t(a.H) << 32) | (uint64_t(sizeof(ST)) << 24) |
+                         (uint64_t(VEC) << 16) | (uint64_t(want) << 8) | uint64_t(nostage);
+    FwdGeom g;
+    bool hit = false;
+    {
+        std::lock_guard<std::mutex> lk(plan->cache_mu);
+        auto it = plan->geom_cache.find(key);
+        if (it != plan->geom_cache.end()) {
+            memcpy(&g, it->second.data(), sizeof(g));
+            hit = true;
+        }
     }
-    int dev = 0, sms = 0;
-    TG_CUDA(cudaGetDevice(&dev));
-    TG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (!hit) {
+        g.npw = 32 / hp;
+        const size_t ybytes = size_t(T) * HC * sizeof(float);
+        g.per = row_period(uint32_t(HC * sizeof(ST)));
+        g.off_meta = 128;
+        g.off_y = 128 + (tl.num_tiles <= kMetaSmemTiles ? tl.num_tiles * 32 : 0);
+        g.off_stage0 = (uint32_t)((g.off_y + ybytes + 127) & ~size_t(127));
+        const StagePick sp = pick_stages(tl, T, HC, sizeof(ST), g.per, g.off_stage0, want);
+        g.num_stages = sp.num_stages > 0 ? sp.num_stages : 1;
+        g.cap_rows = sp.cap_rows;
+        g.cap_k = sp.num_stages > 0 ? sp.cap_k : -1;  // -1: nothing is staged
+        if (nostage) g.cap_k = -1;
+        g.stage_bytes = sp.stage_bytes;
+        g.off_xr = sp.off_xr;
+        g.off_xl = sp.off_xl;
+        g.smem = (uint32_t)(g.off_stage0 + size_t(g.num_stages) * g.stage_bytes);
+        bool all_staged = g.cap_k >= 0;
+        for (int t = 0; t < tl.num_tiles && all_staged; ++t) {
+            const tg_tile_meta &m = tl.h_meta[t];
+            all_staged = m.eligible && m.hi - m.lo <= g.cap_rows && (m.kin_kout & 0xFFFF) <= g.cap_k;
+        }
+        g.all_staged = all_staged;
+        std::lock_guard<std::mutex> lk(plan->cache_mu);
+        auto &blob = plan->geom_cache[key];
+        blob.resize(sizeof(g));
+        memcpy(blob.data(), &g, sizeof(g));
+    }
+    a.npw = g.npw; a.per = g.per; a.num_stages = g.num_stages; a.cap_rows = g.cap_rows; a.cap_k = g.cap_k;
+    a.stage_bytes = g.stage_bytes; a.off_meta = g.off_meta; a.off_stage0 = g.off_stage0; a.off_xr = g.off_xr; a.off_xl = g.off_xl;
+    a.off_y = g.off_y;
+    const size_t smem = g.smem;
+    const bool all_staged = g.all_staged != 0;
+    const int ncw = T / a.npw;  // consumer warps
+    const int sms = tg_sm_count();
     auto go = [&](auto kern) -> int {
-        TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int occ = 1;
-        TG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, (ncw + 1) * 32, smem));
-        if (occ < 1) occ = 1;
-        const int64_t grid = std::min<int64_t>(a.items, int64_t(sms) * occ);
+        TG_CUDA(tg_set_smem(reinterpret_cast<const void *>(kern), (int)smem));
+        // one persistent CTA per SM (512 threads and > 113 KB of shared memory: never two)
+        const int64_t grid = std::min<int64_t>(a.items, int64_t(sms));
         kern<<<(unsigned)grid, (ncw + 1) * 32, smem, st>>>(a);
+        tg_count_launch();
         return TECGAT_OK;
     };
     int rc;
@@ -382,6 +414,13 @@ extern "C" int tecgat_edge_fwd(const tecgat_plan_t *plan, const void *xl, const 
                                const float *bias, float *y, float *stat, int32_t snapshots, int32_t heads,
                                int32_t out_channels, float negative_slope, float dropout_p, uint64_t seed, int32_t mode,
                                int32_t dtype, void *stream) {
+    return tg::edge_fwd_run(plan, xl, xr, att, bias, y, stat, snapshots, heads, out_channels, negative_slope, dropout_p, seed,
+                            nullptr, mode, dtype, stream);
+}
+
+int tg::edge_fwd_run(const tecgat_plan_t *plan, const void *xl, const void *xr, const float *att, const float *bias, float *y,
+                     float *stat, int32_t snapshots, int32_t heads, int32_t out_channels, float negative_slope, float dropout_p,
+                     uint64_t seed, const uint64_t *seed_dev, int32_t mode, int32_t dtype, void *stream) {
     using namespace tg;
     TG_REQUIRE(plan && xl && xr && att && bias && y && stat, TECGAT_EINVAL, "edge_fwd: NULL argument");
     TG_REQUIRE(snapshots > 0 && heads > 0 && out_channels > 0, TECGAT_EINVAL, "edge_fwd: non-positive size");
@@ -408,6 +447,7 @@ extern "C" int tecgat_edge_fwd(const tecgat_plan_t *plan, const void *xl, const 
     a.drop_thr = dropout_p > 0.f ? std::max(1u, dropout_threshold(dropout_p)) : 0u;
     a.inv_keep = 1.f / (1.f - dropout_p);
     a.seed = seed;
+    a.seed_dev = seed_dev;
     a.literal = (mode == TECGAT_MODE_LITERAL);
     a.items = int64_t(tl.num_tiles) * snapshots;
     cudaStream_t st = static_cast<cudaStream_t>(stream);

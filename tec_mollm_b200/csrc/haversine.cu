@@ -169,7 +169,7 @@ extern "C" int tecgraph_distance_rows(const double *lat, const double *lon, int6
     if (r1 == r0) return TECGAT_OK;
     TG_REQUIRE(r1 - r0 <= 65535, TECGAT_EINVAL, "distance_rows: at most 65535 rows per call");
     dim3 grid((unsigned)((n + 255) / 256), (unsigned)(r1 - r0));
-    tg::distance_rows_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(lat, lon, n, r0, r1, radius_km, out);
+    tg::distance_rows_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(lat, lon, n, r0, r1, radius_km, out); tg_count_launch();
     TG_LAUNCH_CHECK();
     return TECGAT_OK;
 }
@@ -227,11 +227,11 @@ extern "C" int tecgraph_edges_count(const double *lat, const double *lon, int64_
     TG_TRY(cudaMemcpyAsync(c->lat, lat, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
     TG_TRY(cudaMemcpyAsync(c->lon, lon, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
     TG_TRY(cudaMemsetAsync(amb_count, 0, sizeof(unsigned int), st));
-    chunk_range_kernel<<<(unsigned)((nchunks + 255) / 256), 256, 0, st>>>(c->lat, n, c->cmin, c->cmax);
+    chunk_range_kernel<<<(unsigned)((nchunks + 255) / 256), 256, 0, st>>>(c->lat, n, c->cmin, c->cmax); tg_count_launch();
     TG_TRY(cudaGetLastError());
     const unsigned blocks = (unsigned)((n * 32 + 255) / 256);
     edges_kernel<false><<<blocks, 256, 0, st>>>(c->lat, c->lon, n, thr_km, radius_km, c->cmin, c->cmax, c->deg, amb, amb_count,
-                                                 nullptr, 0, nullptr, nullptr, nullptr, 0);
+                                                 nullptr, 0, nullptr, nullptr, nullptr, 0); tg_count_launch();
     TG_TRY(cudaGetLastError());
     std::vector<int32_t> deg(n);
     unsigned int namb = 0;
@@ -290,7 +290,7 @@ extern "C" int tecgraph_edges_fill(tecgraph_ctx_t *c, int64_t *edge_index, float
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const unsigned blocks = (unsigned)((c->n * 32 + 255) / 256);
     edges_kernel<true><<<blocks, 256, 0, st>>>(c->lat, c->lon, c->n, c->thr, c->radius, c->cmin, c->cmax, c->deg, nullptr, nullptr,
-                                                c->extra, c->num_extra, c->rowptr, edge_index, edge_weight, c->total);
+                                                c->extra, c->num_extra, c->rowptr, edge_index, edge_weight, c->total); tg_count_launch();
     TG_LAUNCH_CHECK();
     return TECGAT_OK;
 }

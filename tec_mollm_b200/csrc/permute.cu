@@ -75,13 +75,13 @@ static int launch_permute(const float *a, const float *b2, float *out, int B, in
     const dim3 block(bx, by);
     if (vec) {
         auto kern = residual_permute_kernel<float2, FWD>;
-        TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TG_CUDA(tg_set_smem(reinterpret_cast<const void *>(kern), (int)smem));
         kern<<<(unsigned)grid, block, smem, st>>>(reinterpret_cast<const float2 *>(a), reinterpret_cast<const float2 *>(b2),
-                                                reinterpret_cast<float2 *>(out), L, N, C / 2, TN, tiles_per_b);
+                                                reinterpret_cast<float2 *>(out), L, N, C / 2, TN, tiles_per_b); tg_count_launch();
     } else {
         auto kern = residual_permute_kernel<float, FWD>;
-        TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<(unsigned)grid, block, smem, st>>>(a, b2, out, L, N, C, TN, tiles_per_b);
+        TG_CUDA(tg_set_smem(reinterpret_cast<const void *>(kern), (int)smem));
+        kern<<<(unsigned)grid, block, smem, st>>>(a, b2, out, L, N, C, TN, tiles_per_b); tg_count_launch();
     }
     TG_LAUNCH_CHECK();
     return TECGAT_OK;

@@ -27,6 +27,47 @@ void tecgat_set_error(const char *fmt, ...) {
 }
 
 extern "C" const char *tecgat_last_error(void) { return g_last_error.c_str(); }
+
+#include <atomic>
+#include <unordered_map>
+static std::atomic<long long> g_launches{0};
+void tg_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+extern "C" int64_t tecgat_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int tg_sm_count() {
+    static std::mutex mu;
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!cached[dev]) {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+        cached[dev] = sms;
+    }
+    return cached[dev];
+}
+
+cudaError_t tg_set_smem(const void *kernel, int bytes) {
+    static std::mutex mu;
+    static std::unordered_map<uint64_t, int> have;  // (kernel, device) -> largest size already granted
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const uint64_t key = reinterpret_cast<uint64_t>(kernel) * 67u + uint64_t(dev);
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = have.find(key);
+    if (it != have.end() && it->second >= bytes) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) have[key] = bytes;
+    return e;
+}
+
+const char *tg_env(const char *name) {
+    // the knobs are test / tuning switches that tests flip between calls (monkeypatch.setenv), so this is a plain getenv:
+    // ~50 ns per lookup, and the launchers only consult it on a geometry-cache miss
+    return getenv(name);
+}
 extern "C" int tecgat_abi_version(void) { return TECGAT_ABI_VERSION; }
 
 template <typename T>

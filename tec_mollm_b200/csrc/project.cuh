@@ -1,6 +1,7 @@
 // project.cuh -- internal launchers of the two projection implementations (see project.cu for the C ABI).
 #pragma once
 #include "common.cuh"
+#include "reduce.cuh"
 
 namespace tg {
 // CUDA-core cross-check path (project_ffma.cu)
@@ -23,5 +24,5 @@ bool project_bwd_rt_supported(int F, int HC, const void *dxl, const void *dxr, c
 int64_t project_bwd_rt_workspace(int64_t R, int F, int HC);
 int project_bwd_rt(const void *dxl, const void *dxr, const float *x, const float *wl, const float *wr, float *dx, float *dwl,
                    float *dbl, float *dwr, float *dbr, void *workspace, int64_t R, int F, int HC, int dtype, cudaStream_t st,
-                   bool accumulate = false);
+                   bool accumulate = false, ReduceJob *defer = nullptr);
 }  // namespace tg

@@ -310,8 +310,7 @@ __global__ void __launch_bounds__(kThreads, 1) project_bwd_rt_kernel(const Args 
 }
 
 static int grid_for(int64_t R) {
-    int dev = 0, sms = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = tg_sm_count();
     const int64_t tiles = (R + kRows - 1) / kRows;
     return (int)(tiles < sms ? tiles : sms);
 }
@@ -327,16 +326,17 @@ int64_t project_bwd_rt_workspace(int64_t R, int F, int HC) { return int64_t(rt::
 
 int project_bwd_rt(const void *dxl, const void *dxr, const float *x, const float *wl, const float *wr, float *dx, float *dwl,
                    float *dbl, float *dwr, float *dbr, void *workspace, int64_t R, int F, int HC, int dtype, cudaStream_t st,
-                   bool accumulate) {
+                   bool accumulate, ReduceJob *defer) {
     rt::Args a;
     a.accumulate = accumulate ? 1 : 0;
     a.dxl = dxl; a.dxr = dxr; a.x = x; a.wl = wl; a.wr = wr; a.dx = dx; a.partials = static_cast<float *>(workspace);
     a.R = R; a.F = F; a.HC = HC;
     const int grid = rt::grid_for(R);
     auto launch = [&](auto kern, const rt::Smem &L) -> cudaError_t {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+        cudaError_t e = tg_set_smem(reinterpret_cast<const void *>(kern), (int)L.total);
         if (e != cudaSuccess) return e;
         kern<<<grid, rt::kThreads, L.total, st>>>(a);
+        tg_count_launch();
         return cudaSuccess;
     };
     if (HC <= 24) {
@@ -349,6 +349,10 @@ int project_bwd_rt(const void *dxl, const void *dxr, const float *x, const float
     TG_LAUNCH_CHECK();
     const int O = 2 * HC;
     ReduceSegs segs = {{dwl, dwr, dbl, dbr}, {0, HC * F, O * F, O * F + HC}, {HC * F, O * F, O * F + HC, O * F + O}};
+    if (defer) {  // the caller finishes these partials together with the edge kernel's in one launch
+        *defer = ReduceJob{a.partials, grid, O * F + O, segs};
+        return TECGAT_OK;
+    }
     return reduce_columns(a.partials, grid, O * F + O, segs, st);
 }
 

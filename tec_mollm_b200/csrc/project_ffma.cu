@@ -145,12 +145,12 @@ int project_fwd_ffma(const float *x, const float *wl, const float *bl, const flo
     const int grid = ffma_grid(R);
     if (dtype == TECGAT_F32) {
         auto k = project_fwd_ffma_kernel<float>;
-        TG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<grid, kRows, smem, st>>>(x, wl, bl, wr, br, static_cast<float *>(xl), static_cast<float *>(xr), R, F, HC);
+        TG_CUDA(tg_set_smem(reinterpret_cast<const void *>(k), (int)smem));
+        k<<<grid, kRows, smem, st>>>(x, wl, bl, wr, br, static_cast<float *>(xl), static_cast<float *>(xr), R, F, HC); tg_count_launch();
     } else {
         auto k = project_fwd_ffma_kernel<__nv_bfloat16>;
-        TG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<grid, kRows, smem, st>>>(x, wl, bl, wr, br, static_cast<__nv_bfloat16 *>(xl), static_cast<__nv_bfloat16 *>(xr), R, F, HC);
+        TG_CUDA(tg_set_smem(reinterpret_cast<const void *>(k), (int)smem));
+        k<<<grid, kRows, smem, st>>>(x, wl, bl, wr, br, static_cast<__nv_bfloat16 *>(xl), static_cast<__nv_bfloat16 *>(xr), R, F, HC); tg_count_launch();
     }
     TG_LAUNCH_CHECK();
     return TECGAT_OK;
@@ -172,12 +172,12 @@ int project_bwd_ffma(const void *dxl, const void *dxr, const float *x, const flo
     float *partials = static_cast<float *>(workspace);
     if (dtype == TECGAT_F32) {
         auto k = project_bwd_ffma_kernel<float>;
-        TG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<grid, kRows, smem, st>>>(static_cast<const float *>(dxl), static_cast<const float *>(dxr), x, wl, wr, dx, partials, R, F, HC);
+        TG_CUDA(tg_set_smem(reinterpret_cast<const void *>(k), (int)smem));
+        k<<<grid, kRows, smem, st>>>(static_cast<const float *>(dxl), static_cast<const float *>(dxr), x, wl, wr, dx, partials, R, F, HC); tg_count_launch();
     } else {
         auto k = project_bwd_ffma_kernel<__nv_bfloat16>;
-        TG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<grid, kRows, smem, st>>>(static_cast<const __nv_bfloat16 *>(dxl), static_cast<const __nv_bfloat16 *>(dxr), x, wl, wr, dx, partials, R, F, HC);
+        TG_CUDA(tg_set_smem(reinterpret_cast<const void *>(k), (int)smem));
+        k<<<grid, kRows, smem, st>>>(static_cast<const __nv_bfloat16 *>(dxl), static_cast<const __nv_bfloat16 *>(dxr), x, wl, wr, dx, partials, R, F, HC); tg_count_launch();
     }
     TG_LAUNCH_CHECK();
     ReduceSegs segs = {{dwl, dwr, dbl, dbr}, {0, HC * F, O * F, O * F + HC}, {HC * F, O * F, O * F + HC, O * F + O}};

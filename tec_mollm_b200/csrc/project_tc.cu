@@ -363,10 +363,10 @@ static int launch_fwd_tc(TcFwdArgs &a, cudaStream_t st) {
     const TcFwdSmem L = tc_fwd_smem<BF16>(a.F, a.HC, a.KP, a.NP, a.stages);
     TG_REQUIRE(L.total <= 200u * 1024u, TECGAT_ENOSUP, "project_fwd(tc): F=%d, HC=%d needs %u B shared memory", a.F, a.HC, L.total);
     auto kern = project_fwd_tc_kernel<BF16, FT, HT>;
-    TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    TG_CUDA(tg_set_smem(reinterpret_cast<const void *>(kern), (int)L.total));
     const int64_t tiles = (a.R + kTileM - 1) / kTileM;
     const int grid = (int)(tiles < 2 * 148 ? tiles : 2 * 148);
-    kern<<<grid, kTcThreads, L.total, st>>>(a);
+    kern<<<grid, kTcThreads, L.total, st>>>(a); tg_count_launch();
     TG_LAUNCH_CHECK();
     return TECGAT_OK;
 }
@@ -729,9 +729,9 @@ static int launch_bwd_tc(TcBwdArgs &a, float *dwl, float *dbl, float *dwr, float
     bwd_tc_config<SPLIT>(a);
     const TcBwdSmem L = tc_bwd_smem<SPLIT>(a.F, a.HC, a.OP, a.N1, a.NP2, a.stages);
     auto kern = project_bwd_tc_kernel<SPLIT>;
-    TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    TG_CUDA(tg_set_smem(reinterpret_cast<const void *>(kern), (int)L.total));
     const int grid = bwd_tc_grid(a.R);
-    kern<<<grid, kBwdThreads, L.total, st>>>(a);
+    kern<<<grid, kBwdThreads, L.total, st>>>(a); tg_count_launch();
     TG_LAUNCH_CHECK();
     const int O = 2 * a.HC, F = a.F, HC = a.HC;
     ReduceSegs segs = {{dwl, dwr, dbl, dbr}, {0, HC * F, O * F, O * F + HC}, {HC * F, O * F, O * F + HC, O * F + O}};

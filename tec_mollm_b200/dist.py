@@ -45,7 +45,9 @@ class FlatGradAllReduce:
     """Keeps the gradients of ``params`` as views into one flat fp32 buffer and averages it across ranks with a
     single collective."""
 
-    def __init__(self, params: Iterable[torch.nn.Parameter]):
+    def __init__(self, params: Iterable[torch.nn.Parameter], module: torch.nn.Module | None = None):
+        """``module``: when given, every ``GATv2Conv`` inside it is switched to ``fused_grad_accumulation`` -- its backward then
+        adds the parameter gradients straight onto the flat buffer's views (no autograd accumulation kernels)."""
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("no trainable parameters")
@@ -56,6 +58,12 @@ class FlatGradAllReduce:
         for p in self.params:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
             off += p.numel()
+        if module is not None:
+            from .gatv2 import GATv2Conv
+
+            for m in module.modules():
+                if isinstance(m, GATv2Conv):
+                    m.fused_grad_accumulation = True
 
     def zero_(self):
         self.flat.zero_()
@@ -67,6 +75,9 @@ class FlatGradAllReduce:
 
     def all_reduce_mean(self):
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
-            self.flat.div_(dist.get_world_size())
+            if dist.get_backend() == "nccl":  # the mean is taken inside the collective: one launch
+                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)
+            else:
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+                self.flat.div_(dist.get_world_size())
         return self.flat

@@ -24,6 +24,8 @@ from . import _lib
 
 __all__ = ["GATv2Conv", "GraphPlan", "tile_nodes_for"]
 
+_COMPILED_CHANNELS = (1, 2, 3, 4, 5, 6, 7, 8, 11, 12, 16, 24, 32)  # TG_FOR_EACH_C in csrc/edge_common.cuh
+
 
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
@@ -50,18 +52,6 @@ def tile_nodes_for(heads: int, backward: bool = False, out_channels: Optional[in
     knob = os.environ.get("TECGAT_TILE_BWD" if backward else "TECGAT_TILE_FWD")  # tuning knob (benchmarks only)
     t = int(knob) if knob else warps * npw
     return max(npw, min(warps * npw, (t // npw) * npw))
-
-
-# Optional per-phase instrumentation used by bench.py: when set to a list, a CUDA event is recorded on the launching
-# stream after every phase ("proj_fwd", "edge_fwd", "edge_bwd", "proj_bwd"); None (default) costs nothing.
-PHASE_EVENTS = None
-
-
-def _mark(name: str, device):
-    if PHASE_EVENTS is not None:
-        ev = torch.cuda.Event(enable_timing=True)
-        ev.record(torch.cuda.current_stream(device))
-        PHASE_EVENTS.append((name, ev))
 
 
 def _proj_impl() -> int:
@@ -118,31 +108,46 @@ class GraphPlan:
                 pass
 
 
+class _on_device:
+    """``torch.cuda.device(dev)`` only when the calling thread is on another device (the context manager costs ~5 us per
+    use; autograd's worker threads normally already sit on the gradient's device)."""
+
+    __slots__ = ("ctx",)
+
+    def __init__(self, dev: torch.device):
+        self.ctx = None if torch.cuda.current_device() == dev.index else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+
+
 class _GATv2Function(torch.autograd.Function):
-    """forward = project_fwd + edge_fwd; backward = edge_bwd + project_bwd (four launches + two tiny
-    fixed-order reductions).  Saved for backward: x, xl, xr, y, stat (PyG saves 4-6 (S*E, H, C) tensors)."""
+    """forward = ``tecgat_forward`` (projection + fused edge kernel); backward = ``tecgat_backward`` (fused edge backward +
+    projection backward + one fixed-order finish of all six parameter gradients): five launches per training step.
+    Saved for backward: x, xl, xr, y, stat (PyG saves 4-6 (S*E, H, C) tensors)."""
 
     @staticmethod
-    def forward(ctx, x2d, wl, bl, wr, br, att, bias, plan: GraphPlan, S, H, Cc, slope, p, seed, mode, dtype, impl, block=None):
+    def forward(ctx, x2d, wl, bl, wr, br, att, bias, plan: GraphPlan, S, H, Cc, slope, p, seed, seed_t, mode, dtype, impl,
+                block=None, owner=None):
         # block = (B, L): x2d is the (B, L, N, F) tensor flattened; return the whole spatial block of tec_mollm.py:84-106,
         # z[b, n, l, :] = x[b, l, n, :] + y[b, l, n, :], instead of y (SURVEY.md 8f N1)
         dev = x2d.device
         R, F = x2d.shape
         HC = H * Cc
         st_dtype = torch.float32 if dtype == _lib.F32 else torch.bfloat16
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             stream = _stream(dev)
             xl = torch.empty((R, HC), device=dev, dtype=st_dtype)
             xr = torch.empty((R, HC), device=dev, dtype=st_dtype)
             y = torch.empty((R, HC), device=dev, dtype=torch.float32)
             stat = torch.empty((R, H), device=dev, dtype=torch.float32)
-            _mark("start_fwd", dev)
-            _lib.call("tecgat_project_fwd", _ptr(x2d), _ptr(wl), _ptr(bl), _ptr(wr), _ptr(br), _ptr(xl), _ptr(xr),
-                      R, F, HC, dtype, impl, stream)
-            _mark("proj_fwd", dev)
-            _lib.call("tecgat_edge_fwd", plan.handle, _ptr(xl), _ptr(xr), _ptr(att), _ptr(bias), _ptr(y), _ptr(stat),
-                      S, H, Cc, slope, p, seed, mode, dtype, stream)
-            _mark("edge_fwd", dev)
+            _lib.call("tecgat_forward", plan.handle, _ptr(x2d), _ptr(wl), _ptr(bl), _ptr(wr), _ptr(br), _ptr(att), _ptr(bias),
+                      _ptr(xl), _ptr(xr), _ptr(y), _ptr(stat), S, F, H, Cc, slope, p, seed, _ptr(seed_t), mode, dtype, impl, stream)
             out = y
             if block is not None:
                 B, L = block
@@ -151,7 +156,9 @@ class _GATv2Function(torch.autograd.Function):
         ctx.save_for_backward(x2d, wl, wr, att, bias, xl, xr, y, stat)
         ctx.plan = plan
         ctx.cfg = (S, H, Cc, slope, p, seed, mode, dtype, impl)
+        ctx.seed_t = seed_t
         ctx.block = block
+        ctx.owner = owner
         return out
 
     @staticmethod
@@ -168,47 +175,48 @@ class _GATv2Function(torch.autograd.Function):
         block = ctx.block
         if block is None and gy.data_ptr() % 16:  # bulk-TMA sources are 16-byte aligned
             gy = gy.clone()
-        with torch.cuda.device(dev):  # autograd worker threads do not inherit the current device
+        L = _lib.lib()
+        with _on_device(dev):  # autograd worker threads do not always inherit the current device
             stream = _stream(dev)
             if block is not None:  # gy arrives as (B, N, L, HC): one transposition gives the gradient of y AND of the residual
-                B, L = block
+                B, Lb = block
                 g = torch.empty((R, HC), device=dev, dtype=torch.float32)
-                _lib.call("tecgat_residual_permute_bwd", _ptr(gy), _ptr(g), B, L, R // S, HC, stream)
+                _lib.call("tecgat_residual_permute_bwd", _ptr(gy), _ptr(g), B, Lb, R // S, HC, stream)
                 gy = g
             dxl = torch.empty_like(xl)
             dxr = torch.empty_like(xr)
-            datt = torch.empty((1, H, Cc), device=dev, dtype=torch.float32)
-            dbias = torch.empty((HC,), device=dev, dtype=torch.float32)
-            ws1 = torch.empty((max(1, _lib.lib().tecgat_edge_bwd_workspace(plan.handle, S, H, Cc)),), device=dev,
-                              dtype=torch.uint8)
-            dx = torch.empty_like(x2d) if ctx.needs_input_grad[0] and block is None else None
-            # block: dx = g + dxl Wl + dxr Wr accumulates in place into g (nobody reads gy after edge_bwd)
-            acc = (block is not None and ctx.needs_input_grad[0] and impl == _lib.PROJ_TC
-                   and _lib.lib().tecgat_project_bwd_acc_supported(F, HC) == 1)
-            if block is not None and ctx.needs_input_grad[0] and not acc:
-                dx = torch.empty_like(x2d)
-            dwl = torch.empty_like(wl)
-            dwr = torch.empty_like(wr)
-            dbl = torch.empty((HC,), device=dev, dtype=torch.float32)
-            dbr = torch.empty((HC,), device=dev, dtype=torch.float32)
-            ws2 = torch.empty((max(1, _lib.lib().tecgat_project_bwd_workspace(R, F, HC, impl)),), device=dev,
-                              dtype=torch.uint8)
-            _mark("start_bwd", dev)
-            _lib.call("tecgat_edge_bwd", plan.handle, _ptr(xl), _ptr(xr), _ptr(att), _ptr(bias), _ptr(y), _ptr(stat),
-                      _ptr(gy), _ptr(dxl), _ptr(dxr), _ptr(datt), _ptr(dbias), _ptr(ws1), S, H, Cc, slope, p,
-                      seed, mode, dtype, stream)
-            _mark("edge_bwd", dev)
-            if acc:
-                _lib.call("tecgat_project_bwd_acc", _ptr(dxl), _ptr(dxr), _ptr(x2d), _ptr(wl), _ptr(wr), _ptr(gy), _ptr(dwl),
-                          _ptr(dbl), _ptr(dwr), _ptr(dbr), _ptr(ws2), R, F, HC, dtype, stream)
-                dx = gy
-            else:
-                _lib.call("tecgat_project_bwd", _ptr(dxl), _ptr(dxr), _ptr(x2d), _ptr(wl), _ptr(wr), _ptr(dx), _ptr(dwl),
-                          _ptr(dbl), _ptr(dwr), _ptr(dbr), _ptr(ws2), R, F, HC, dtype, impl, stream)
-                if block is not None and dx is not None:
-                    dx += gy
-            _mark("proj_bwd", dev)
-        return (dx, dwl, dbl, dwr, dbr, datt, dbias) + (None,) * 11
+            need_dx = ctx.needs_input_grad[0]
+            aligned = not (x2d.data_ptr() | xl.data_ptr() | xr.data_ptr() | dxl.data_ptr() | dxr.data_ptr() | gy.data_ptr()) & 15
+            fused_ok = aligned and L.tecgat_backward_fused_supported(F, HC, impl) == 1
+            # block: dx = g + dxl Wl + dxr Wr accumulates in place into g (nobody reads gy after the edge kernel)
+            dx_acc = block is not None and need_dx and fused_ok
+            dx = gy if dx_acc else (torch.empty_like(x2d) if need_dx else None)
+            # parameter gradients: straight onto the owner's .grad storage when it asked for that (fused_grad_accumulation) and
+            # every .grad exists -- replaces autograd's six accumulation kernels; otherwise fresh tensors returned to autograd
+            owner = ctx.owner
+            grads = None
+            if fused_ok and owner is not None and owner.fused_grad_accumulation:
+                params = (owner.lin_l.weight, owner.lin_l.bias, owner.lin_r.weight, owner.lin_r.bias, owner.att, owner.bias)
+                gs = [q.grad for q in params]
+                if all(t is not None and t.dtype == torch.float32 and t.is_contiguous() and t.device == dev for t in gs):
+                    grads = gs
+            acc = grads is not None
+            if not acc:
+                grads = [torch.empty_like(wl), torch.empty((HC,), device=dev, dtype=torch.float32), torch.empty_like(wr),
+                         torch.empty((HC,), device=dev, dtype=torch.float32),
+                         torch.empty((1, H, Cc), device=dev, dtype=torch.float32),
+                         torch.empty((HC,), device=dev, dtype=torch.float32)]
+            dwl, dbl, dwr, dbr, datt, dbias = grads
+            ws = torch.empty((max(1, L.tecgat_backward_workspace(plan.handle, S, F, H, Cc, impl)),), device=dev, dtype=torch.uint8)
+            _lib.call("tecgat_backward", plan.handle, _ptr(x2d), _ptr(wl), _ptr(wr), _ptr(att), _ptr(bias), _ptr(xl), _ptr(xr),
+                      _ptr(y), _ptr(stat), _ptr(gy), _ptr(dxl), _ptr(dxr), _ptr(dx), int(dx_acc), _ptr(dwl), _ptr(dbl), _ptr(dwr),
+                      _ptr(dbr), _ptr(datt), _ptr(dbias), int(acc), _ptr(ws), S, F, H, Cc, slope, p, seed, _ptr(ctx.seed_t), mode,
+                      dtype, impl, stream)
+            if block is not None and need_dx and not dx_acc:
+                dx += gy
+        if acc:
+            return (dx,) + (None,) * 19
+        return (dx, dwl, dbl, dwr, dbr, datt, dbias) + (None,) * 13
 
 
 class _Linear(nn.Module):
@@ -264,14 +272,33 @@ class GATv2Conv(nn.Module):
         self.lin_r = _Linear(in_channels, heads * out_channels)
         self.att = nn.Parameter(torch.empty(1, heads, out_channels))
         self.bias = nn.Parameter(torch.empty(heads * out_channels))
+        if heads < 1 or heads > 32:
+            raise NotImplementedError(f"GATv2Conv (tec_mollm_b200): heads={heads} outside the compiled range 1..32")
+        if out_channels not in _COMPILED_CHANNELS:
+            raise NotImplementedError(f"GATv2Conv (tec_mollm_b200): out_channels={out_channels} is not among the compiled "
+                                      f"channel counts {_COMPILED_CHANNELS}")
         self._plans = {}
+        # opt-in: backward adds the parameter gradients straight onto existing .grad storage and returns None for them
+        # (no autograd accumulation kernels).  Leave it off under DistributedDataParallel, whose hooks need autograd's own
+        # accumulation; tec_mollm_b200.dist.FlatGradAllReduce switches it on.
+        self.fused_grad_accumulation = False
+        self._last_seed = None
+        self._rng_state = None  # device int64[2] = {seed, counter}: the attention-dropout stream (see _dropout_state)
         self._tile_nodes = tile_nodes_for(heads)
         self._tile_nodes_bwd = tile_nodes_for(heads, backward=True, out_channels=out_channels)
+        hp = 1
+        while hp < heads:
+            hp *= 2
+        if 2 * heads * out_channels > self._tile_nodes_bwd * hp:  # the backward's gradient flush maps 2*H*C columns onto its threads
+            raise NotImplementedError(f"GATv2Conv (tec_mollm_b200): heads*out_channels = {heads * out_channels} exceeds what the "
+                                      f"backward kernel's {self._tile_nodes_bwd * hp} consumer threads reduce")
         self.reset_parameters()
 
     def __getstate__(self):  # graph plans hold device handles: never pickled / deep-copied
         state = self.__dict__.copy()
         state["_plans"] = {}
+        state["_rng_state"] = None
+        state["_last_seed"] = None
         return state
 
     def reset_parameters(self):
@@ -294,9 +321,17 @@ class GATv2Conv(nn.Module):
         self._plans[key] = (plan, edge_index)  # keep the tensor alive so its data_ptr cannot be recycled
         return plan
 
-    def _dropout_seed(self, device) -> int:
-        # drawn from torch's CPU generator: reproducible under torch.manual_seed, no device sync
-        return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+    def _dropout_state(self, device) -> torch.Tensor:
+        """Device-resident state {seed, counter} of the attention-dropout stream.  The seed is drawn ONCE from torch's CPU
+        generator (reproducible under ``torch.manual_seed``, no device sync); every training forward then advances the
+        counter on the device (``tecgat_seed_advance``), so nothing on the host is consumed per step and a captured CUDA graph
+        draws a fresh mask on every replay."""
+        st = self._rng_state
+        if st is None or st.device != device:
+            seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+            st = torch.tensor([seed, 0], dtype=torch.int64, device=device)
+            self._rng_state = st
+        return st
 
     def forward_snapshots(self, x: torch.Tensor, edge_index: torch.Tensor, snapshots: int, num_nodes: int,
                           snapshot_mode: str = "shared", seed: Optional[int] = None, block=None) -> torch.Tensor:
@@ -320,14 +355,18 @@ class GATv2Conv(nn.Module):
             x = x.float()
         plan = self.plan_for(edge_index, num_nodes)
         p = self.dropout if self.training else 0.0
-        if p > 0.0 and seed is None:
-            seed = self._dropout_seed(x.device)
+        seed_t = None
+        if p > 0.0 and seed is None:  # an explicit ``seed`` (tests: reproduce the mask on the host) is passed by value
+            seed_t = torch.empty(1, dtype=torch.int64, device=x.device)
+            with _on_device(x.device):
+                _lib.call("tecgat_seed_advance", _ptr(self._dropout_state(x.device)), _ptr(seed_t), _stream(x.device))
+            self._last_seed = seed_t  # tests rebuild the kernels' mask on the host from it
         mode = _lib.MODE_SHARED if snapshot_mode == "shared" else _lib.MODE_LITERAL
         f32 = lambda t: t if t.dtype == torch.float32 else t.float()
         return _GATv2Function.apply(
             x, f32(self.lin_l.weight), f32(self.lin_l.bias), f32(self.lin_r.weight), f32(self.lin_r.bias),
             f32(self.att), f32(self.bias), plan, int(snapshots), self.heads, self.out_channels,
-            self.negative_slope, float(p), int(seed or 0), mode, dtype, _proj_impl(), block)
+            self.negative_slope, float(p), int(seed or 0), seed_t, mode, dtype, _proj_impl(), block, self)
 
     def forward(self, x: torch.Tensor, edge_index: torch.Tensor, edge_attr=None, return_attention_weights=None):
         """PyG semantics for one 2-D input: ``num_nodes = x.size(0)`` rows, edges as given (so calling it the way

@@ -23,9 +23,19 @@ from .gatv2 import GATv2Conv
 class SpatialEncoder(nn.Module):
     """Captures spatial dependencies using a GATv2 layer (hand-written sm_100a kernels)."""
 
+    _warned_default_mode = False
+
     def __init__(self, in_channels: int, out_channels: int, heads: int = 2, dropout: float = 0.1,
-                 snapshot_mode: str = "shared"):
+                 snapshot_mode: str = None):
         super().__init__()
+        if snapshot_mode is None:
+            snapshot_mode = "shared"
+            if not SpatialEncoder._warned_default_mode:  # once per process: the default is NOT what the reference computes
+                SpatialEncoder._warned_default_mode = True
+                logging.warning(
+                    "tec_mollm_b200.SpatialEncoder: snapshot_mode defaults to 'shared' (the graph is applied to every one of the "
+                    "B*L snapshots, the semantics tec_mollm.py:86-88 intends). The reference's own call (modules.py:353-356) gives "
+                    "edges to snapshot 0 only; pass snapshot_mode='literal' to reproduce a reference-trained checkpoint's outputs.")
         if snapshot_mode not in ("shared", "literal"):
             raise ValueError(f"snapshot_mode must be 'shared' or 'literal'; got {snapshot_mode!r}")
         self.gat_conv = GATv2Conv(in_channels, out_channels, heads=heads, dropout=dropout, concat=True,
@@ -74,3 +84,32 @@ class SpatialEncoder(nn.Module):
         B, L, N, Cc = x.shape
         z = self.gat_conv.forward_snapshots(x.reshape(-1, Cc), edge_index, B * L, N, "shared", block=(B, L))
         return z.view(B * N, L, Cc)
+
+    def graphed(self, sample_x: torch.Tensor, edge_index: torch.Tensor, block: bool = False):
+        """Opt-in CUDA-graph mode for small batches (the reference trains at B = 2, train.py:182, where the eager step is
+        host-launch bound): returns a callable ``f(x) -> y`` whose forward and backward each replay one captured CUDA graph
+        (``torch.cuda.make_graphed_callables``).  ``x`` must keep ``sample_x``'s shape, dtype and ``requires_grad``;
+        ``edge_index`` is bound at capture.  Parameter gradients reach ``.grad`` as usual; attention dropout stays correct
+        under replay because its seed lives on the device (``tecgat_seed_advance``).  ``block=True`` graphs
+        :meth:`forward_block` instead of :meth:`forward`."""
+        if not sample_x.is_cuda:
+            raise RuntimeError("SpatialEncoder.graphed needs CUDA tensors (there is no CPU path)")
+        if self.gat_conv.fused_grad_accumulation:
+            raise RuntimeError("graphed(): fused_grad_accumulation writes onto .grad storage that a captured graph would pin; "
+                               "switch it off (the graphed callable returns gradients through autograd)")
+        enc = self
+
+        class _Bound(nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.enc = enc
+
+            def forward(self, x):
+                return enc.forward_block(x, edge_index) if block else enc(x, edge_index)
+
+        with torch.no_grad():  # the plan is built outside capture (plan creation synchronises once)
+            num_nodes = sample_x.shape[-2]
+            self.gat_conv.plan_for(edge_index, num_nodes)
+            if self.training and self.gat_conv.dropout > 0:
+                self.gat_conv._dropout_state(sample_x.device)
+        return torch.cuda.make_graphed_callables(_Bound(), (sample_x,))

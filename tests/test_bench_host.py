@@ -29,3 +29,23 @@ def test_gpu_local_cpus_restores_affinity_and_never_raises():
     with b.gpu_local_cpus(0) as bound:
         assert bound in (True, False)  # no GPU / no NVML here: False, and no exception
     assert os.sched_getaffinity(0) == before
+
+
+def test_workload_table_and_reference_arm_config():
+    """Every --config names its BASELINE row, and the grids are the ones the graph goldens were generated on."""
+    import numpy as np
+
+    b = _bench()
+    assert set(b.CONFIGS) == {"default", "dense300h4", "global64k"}
+    lat, lon = b.grid_axes(b.CONFIGS["default"])
+    assert lat.size == 41 and lon.size == 71 and lat[0] == 15.0 and lon[-1] == 140.0
+    g = np.load(os.path.join(ROOT, "tests", "golden", "graph_cn150.npz"))
+    assert np.array_equal(lat, g["lat"]) and np.array_equal(lon, g["lon"])
+    glat, glon = b.grid_axes(b.CONFIGS["global64k"])
+    assert glat.size * glon.size == 64800 and glat[0] == -89.5 and glon[-1] == 179.5
+
+    class A:
+        config, scaling, batch, dropout, autocast = "dense300h4", "strong", 64, 0.1, False
+
+    c = b.workload_config(A, b.CONFIGS["dense300h4"], 8, 8)
+    assert c["global_batch"] == 64 and "300 km" in c["workload"] and c["name"] == "dense300h4"

@@ -313,9 +313,8 @@ def test_dropout_with_the_kernels_own_mask(cuda_device, mode):
     ei = random_graph(N, 400, seed=12)
     x, gy, p = _rand_case(S, N, F, H, C, seed=13)
     enc = _encoder(F, H, C, p, cuda_device, mode, dropout=p_drop).train()
-    seed = 987654321
-    enc.gat_conv._dropout_seed = lambda device: seed
     y, grads = _run_cuda(enc, x, ei, gy)
+    seed = int(enc.gat_conv._last_seed.item()) & (2 ** 64 - 1)  # drawn on the device (tecgat_seed_advance)
     plan = next(iter(enc.gat_conv._plans.values()))[0]
     mask = kernel_dropout_mask(plan, S, H, p_drop, seed, mode).double()
     assert 0.15 < 1.0 - mask.mean().item() < 0.35

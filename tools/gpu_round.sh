@@ -18,6 +18,8 @@ if [[ "$WHAT" == *" tests "* ]]; then
   run fused_ffma "TECGAT_PROJ=ffma" tests/test_gpu_gatv2.py -k "not plan and not projection"
   run fused_tc "TECGAT_PROJ=tc" tests/test_gpu_gatv2.py -k "not plan and not projection"
   run graph "TECGAT_PROJ=tc" tests/test_gpu_graph.py
+  run round2 "TECGAT_PROJ=tc" tests/test_gpu_round2.py -s
+  grep -E "unpinned|bf16 training" $OUT/test_round2.log | head -20
   timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1; echo "== smoke: exit $? :: $(tail -1 $OUT/smoke.log)"
 fi
 if [[ "$WHAT" == *" bench "* ]]; then
@@ -28,7 +30,9 @@ try:
     d = json.load(open("gpurun_out/bench_tc.json"))
     print("value %.3e edge-msgs/s  ms/step %.3f  e2e %.3e" % (d["value"], d["ms_per_step"], d["e2e"]["value"]))
     for k, v in d["phases"].items(): print("  %-9s %7.3f ms  %6.0f GB/s  frac %.3f" % (k, v["ms"], v["achieved_gbs"], v["frac"]))
-    print("  clocks", d["clocks"], "cpu", d.get("cpu_baseline", {}).get("value"))
+    print("  clocks", d["clocks"], "cpu", d.get("cpu_baseline", {}).get("value"), "launches/step", d.get("gpu_launches_per_step_per_rank"))
+    print("  other", json.dumps(d.get("other_configs")))
+    print("  graph_build", json.dumps(d.get("graph_build")))
 except Exception as e: print("bench parse failed", e)
 PY
   timeout 600 python bench.py --steps 10 --warmup 3 --autocast --no-cpu-baseline > $OUT/bench_bf16.json 2> $OUT/bench_bf16.err; echo "== bench bf16: exit $?"
@@ -41,6 +45,19 @@ try:
 except Exception as e: print("bench parse failed", e)
 PY
   timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; echo "== bench reference: exit $?"
+fi
+if [[ "$WHAT" == *" configs "* ]]; then
+  for c in dense300h4 global64k; do
+    timeout 900 python bench.py --config $c --steps 5 --warmup 3 > $OUT/bench_$c.json 2> $OUT/bench_$c.err; echo "== bench $c: exit $?"
+    python - $c <<'PY'
+import json, sys
+try:
+    d = json.load(open("gpurun_out/bench_%s.json" % sys.argv[1]))
+    print("%s: value %.3e  ms/step %.3f  whole-path frac %.3f  graph_build %.2f ms" % (sys.argv[1], d["value"], d["ms_per_step"], d["whole_path_frac_of_roofline"], d["graph_build"]["ms"]))
+    for k, v in d["phases"].items(): print("  %-9s %7.3f ms  %6.0f GB/s  frac %.3f" % (k, v["ms"], v["achieved_gbs"], v["frac"]))
+except Exception as e: print("bench parse failed", e)
+PY
+  done
 fi
 SMALL="python bench.py --steps 2 --warmup 3 --batch 16 --no-cpu-baseline"
 if [[ "$WHAT" == *" ncu "* ]]; then
