@@ -399,19 +399,42 @@ def run_gpu_arm(args):
         if not ar_check["ok"]:
             raise RuntimeError(f"all-reduced gradient differs from the mean of the per-rank gradients: {err:.3e}")
 
-    # ---- e2e: x from pinned host memory every step (double-buffered), gradients read back ----------------------
+    # ---- e2e: RAW features from pinned host memory every step (double-buffered), gradients read back -------------------
+    # What the reference moves per step (train.py:58-65): x (B, L, N, 6) and the (B, L, 4) time features.  The public call is
+    # the two drop-in modules, SpatioTemporalEmbedding (fused gather + concat) -> SpatialEncoder; its backward also reduces the
+    # embedding-table gradients, so this step does MORE than the device-timed one.
+    from tec_mollm_b200 import SpatioTemporalEmbedding
+
+    C_RAW = 6
+    D_EMB = F_IN - C_RAW
+    emb = SpatioTemporalEmbedding(D_EMB, num_nodes=N_NODES).to(dev).train()
     with gpu_local_cpus(local_rank) as numa_bound:  # pinned pages land on the GPU's own NUMA node (first touch)
-        x_host = [torch.randn(S, N_NODES, F_IN).pin_memory() for _ in range(2)]
-    x_dev = [torch.empty(S, N_NODES, F_IN, device=dev).requires_grad_(True) for _ in range(2)]
-    g_host = torch.empty(flat.flat.numel()).pin_memory()
+        x_host = [torch.randn(B, L_IN, N_NODES, C_RAW).pin_memory() for _ in range(2)]
+        tf_host = [torch.stack([torch.randint(0, 12, (B, L_IN)), torch.randint(0, 366, (B, L_IN)), torch.randint(0, 13, (B, L_IN)),
+                                torch.randint(0, 4, (B, L_IN))], dim=-1).float().pin_memory() for _ in range(2)]
+    x_dev = [torch.empty(B, L_IN, N_NODES, C_RAW, device=dev) for _ in range(2)]
+    tf_dev = [torch.empty(B, L_IN, 4, device=dev) for _ in range(2)]
+    gy4 = gy.view(B, L_IN, N_NODES, HEADS * C_OUT)
+    emb_params = list(emb.parameters())
+    g_host = torch.empty(flat.flat.numel() + sum(p.numel() for p in emb_params)).pin_memory()
     copy_stream = torch.cuda.Stream(dev)
     main = torch.cuda.current_stream(dev)
     ready = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
 
+    def e2e_step(i):
+        flat.zero_()
+        for p in emb_params:
+            p.grad = None
+        with torch.autocast("cuda", dtype=torch.bfloat16) if args.autocast else contextlib.nullcontext():
+            y = enc(emb(x_dev[i], tf_dev[i]), ei)      # (B, L, N, 22): snapshots in (b, l) order, no permute copy needed
+        y.backward(gy4)
+        flat.all_reduce_mean()
+
     def e2e_loop(n):
         with torch.cuda.stream(copy_stream):
-            x_dev[0].data.copy_(x_host[0], non_blocking=True)
+            x_dev[0].copy_(x_host[0], non_blocking=True)
+            tf_dev[0].copy_(tf_host[0], non_blocking=True)
             ready[0].record(copy_stream)
         for i in range(n):
             cur, nxt = i & 1, (i + 1) & 1
@@ -419,12 +442,18 @@ def run_gpu_arm(args):
                 with torch.cuda.stream(copy_stream):
                     if i >= 1:
                         copy_stream.wait_event(consumed[nxt])
-                    x_dev[nxt].data.copy_(x_host[nxt], non_blocking=True)
+                    x_dev[nxt].copy_(x_host[nxt], non_blocking=True)
+                    tf_dev[nxt].copy_(tf_host[nxt], non_blocking=True)
                     ready[nxt].record(copy_stream)
             main.wait_event(ready[cur])
-            step(x_dev[cur])
+            e2e_step(cur)
             consumed[cur].record(main)
-            g_host.copy_(flat.flat, non_blocking=True)
+            nflat = flat.flat.numel()
+            g_host[:nflat].copy_(flat.flat, non_blocking=True)
+            off = nflat
+            for p in emb_params:  # the embedding tables' gradients leave with the encoder's (47k floats)
+                g_host[off:off + p.numel()].copy_(p.grad.view(-1), non_blocking=True)
+                off += p.numel()
         main.synchronize()
 
     e2e_loop(min(2, args.warmup))
@@ -436,6 +465,7 @@ def run_gpu_arm(args):
     t1.record()
     barrier()
     e2e_ms = t0.elapsed_time(t1)
+    h2d_per_rank = x_host[0].numel() * 4 + tf_host[0].numel() * 4
 
     # ---- max over ranks; totals over ranks -----------------------------------------------------------------------
     stats = torch.tensor([elapsed_ms, e2e_ms, ar_ms] + [phase_ms[k] for k in names], device=dev, dtype=torch.float64)
@@ -475,9 +505,12 @@ def run_gpu_arm(args):
             "phases": phases,
             "whole_path_frac_of_roofline": (rows * sum(bpr.values()) / (step_ms * 1e-3) / 1e9) / peak,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
-                    "h2d_bytes_per_step": int(total_snapshots) * N_NODES * F_IN * 4, "d2h_bytes_per_step": world * g_host.numel() * 4,
+                    "h2d_bytes_per_step": int(h2d_per_rank * total_snapshots / S), "d2h_bytes_per_step": world * g_host.numel() * 4,
                     "host_buffers_numa_local": bool(numa_bound),
-                    "note": "y and dx stay on the device (training consumes them there); only x crosses H2D and the flat parameter gradient D2H"},
+                    "call": "SpatioTemporalEmbedding(x_raw, time_features) -> SpatialEncoder(.., edge_index) -> backward",
+                    "note": "raw (B, L, N, 6) features + (B, L, 4) time indices cross H2D (what train.py:58-65 copies); the embedding "
+                            "gather + concat runs on the device; y and dx stay on the device (training consumes them there); the "
+                            "encoder's and the embedding tables' gradients are read back D2H"},
             "gpu_launches": total_launches,
             "gpu_launches_per_step_per_rank": launches / args.steps,
             "allreduce": {"ms_per_step": ar_ms, "bytes": flat.flat.numel() * 4, "share_of_step": ar_ms / step_ms if step_ms else 0.0,

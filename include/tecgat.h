@@ -173,6 +173,26 @@ int tecgat_residual_permute_fwd(const float *x_dev, const float *y_dev, float *z
 int tecgat_residual_permute_bwd(const float *gz_dev, float *g_dev, int32_t batch, int32_t steps,
                                 int32_t nodes, int32_t channels, void *stream);
 
+/* ---- producer side of the spatial block: replaces SpatioTemporalEmbedding.forward
+ *      (src/model/modules.py:230-264: five embedding gathers, four adds, one concat) and its autograd backward.
+ *        out[s, n, 0:Cr]     = x[s, n, :]
+ *        out[s, n, Cr:Cr+De] = node[n] + (((tod[tf[s,0]] + doy[tf[s,1]]) + year[tf[s,2]]) + season[tf[s,3]])
+ *      (the reference's association order: bit-identical to torch).  tf_dev: (S, 4) int32, one row per snapshot -- the
+ *      reference's time features are per (batch, step) and only EXPANDED over the nodes (train.py:64-65).  Indices are
+ *      clamped to the table.  x (S, N, Cr), out (S, N, Cr+De), tables (rows, De): fp32, contiguous.
+ *      tecgat_embed_bwd: ge = d out; d node[n] = sum_s ge[s, n, Cr:], d tab[i] = sum over the snapshots that index row i of
+ *      sum_n ge[s, n, Cr:]; fixed-order fp64 reductions, no atomics (torch's embedding backward is atomic);
+ *      accumulate = 1 adds onto the buffers.  Needs De = 16 (the reference's d_emb) and an even Cr. */
+int tecgat_embed_fwd(const float *x_dev, const int32_t *tf_dev, const float *node_dev, const float *tod_dev,
+                     const float *doy_dev, const float *year_dev, const float *season_dev, float *out_dev,
+                     int32_t snapshots, int32_t nodes, int32_t raw_channels, int32_t emb_dim, int32_t n_tod,
+                     int32_t n_doy, int32_t n_year, int32_t n_season, void *stream);
+int64_t tecgat_embed_bwd_workspace(int32_t snapshots, int32_t nodes, int32_t emb_dim);
+int tecgat_embed_bwd(const float *ge_dev, const int32_t *tf_dev, float *dnode_dev, float *dtod_dev,
+                     float *ddoy_dev, float *dyear_dev, float *dseason_dev, void *workspace_dev,
+                     int32_t snapshots, int32_t nodes, int32_t raw_channels, int32_t emb_dim, int32_t n_tod,
+                     int32_t n_doy, int32_t n_year, int32_t n_season, int32_t accumulate, void *stream);
+
 /* ---- graph builder: replaces calculate_haversine_distance_matrix (src/graph/graph_constructor.py:34-59,
  *      sklearn haversine_distances in fp64), construct_binary_adjacency (:61-81, inclusive `<=`, zero
  *      diagonal), symmetrically_normalize_adjacency (:99-128) and the COO extraction of

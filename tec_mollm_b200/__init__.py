@@ -3,7 +3,8 @@ graph builder.  Python here is plumbing (tensors, autograd wiring, torch.distrib
 computed by the hand-written CUDA library ``lib/libtecgat.so`` behind the C ABI in ``include/tecgat.h``."""
 from .gatv2 import GATv2Conv, GraphPlan, tile_nodes_for  # noqa: F401
 from .spatial_encoder import SpatialEncoder  # noqa: F401
+from .embedding import SpatioTemporalEmbedding  # noqa: F401
 from . import graph  # noqa: F401
 from . import dist  # noqa: F401
 
-__all__ = ["GATv2Conv", "GraphPlan", "SpatialEncoder", "graph", "dist", "tile_nodes_for"]
+__all__ = ["GATv2Conv", "GraphPlan", "SpatialEncoder", "SpatioTemporalEmbedding", "graph", "dist", "tile_nodes_for"]

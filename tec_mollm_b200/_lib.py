@@ -48,6 +48,9 @@ _SIGNATURES = {
     "tecgat_launch_count": (_i64, []),
     "tecgat_phase_timing": (C.c_int, [_i32]),
     "tecgat_phase_times": (C.c_int, [_vp]),
+    "tecgat_embed_fwd": (C.c_int, [_vp] * 8 + [_i32] * 8 + [_vp]),
+    "tecgat_embed_bwd_workspace": (_i64, [_i32, _i32, _i32]),
+    "tecgat_embed_bwd": (C.c_int, [_vp] * 8 + [_i32] * 9 + [_vp]),
     "tecgat_residual_permute_fwd": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "tecgat_residual_permute_bwd": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "tecgat_dropout_mask_host": (C.c_int, [_u64, _i64, _i64, _i32, _f32, _i64, _vp]),

@@ -62,13 +62,19 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
 
     def compile_one(src):
+        # incremental: an object is rebuilt only when its source or any header changed
         obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
+        ostamp, owant = obj + ".sha256", _digest([src] + headers)
+        if not force and os.path.exists(obj) and os.path.exists(ostamp) and open(ostamp).read().strip() == owant:
+            return obj
         cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
         if verbose:
             sys.stderr.write(r.stderr)
+        with open(ostamp, "w") as f:
+            f.write(owant)
         return obj
 
     with ThreadPoolExecutor(max_workers=min(8, len(sources))) as ex:

@@ -176,22 +176,28 @@ def test_bf16_autocast_reference_shape_training(cuda_device):
     eid = eid.astype(np.int64)
     p64 = {k: v.double() for k, v in p.items()}
     tot = {k: torch.zeros_like(v) for k, v in p64.items()}
+    tot_ac = {k: torch.zeros_like(v) for k, v in p64.items()}
     for s in pick:
         m = np.empty((E, H), dtype=np.float32)
         m[np.where(eid >= kept, kept + (eid - kept), eid)] = keep[s]   # one-snapshot oracle order: kept edges, then self loops
         mask = torch.from_numpy(m).double()
-        y_ac, _ = G.fwd_bwd(x[s:s + 1], ei, p, H, C, gy[s:s + 1], autocast_bf16=True, edge_mask=mask.float(), p=p_drop)
+        y_ac, g_ac = G.fwd_bwd(x[s:s + 1], ei, p, H, C, gy[s:s + 1], autocast_bf16=True, edge_mask=mask.float(), p=p_drop)
         y64, g64 = G.fwd_bwd(x[s:s + 1].double(), ei, p64, H, C, gy[s:s + 1].double(), edge_mask=mask, p=p_drop)
         assert rel_err(y[s:s + 1], y_ac) <= TOL_BF16, s
         assert rel_err(y[s:s + 1], y64) <= TOL_BF16, s
-        assert rel_err(grads["x"][s:s + 1], g64["x"]) <= TOL_BF16, s
+        # gradients: bf16 rounding of xl / xr flips LeakyReLU branches, so PyG-autocast itself sits percent-level away from the
+        # fp64 truth; the gate is "within 1e-2 of the truth, or at least as close to it as PyG's own dtype flow" (25 % margin)
+        ours, theirs = rel_err(grads["x"][s:s + 1], g64["x"]), rel_err(g_ac["x"], g64["x"])
+        print(f"bf16 training dx snapshot {s}: ours vs fp64 {ours:.3e}; PyG-autocast vs fp64 {theirs:.3e}")
+        assert ours <= max(TOL_BF16, 1.25 * theirs), (s, ours, theirs)
         for k in tot:
             tot[k] += g64[k]
+            tot_ac[k] += g_ac[k].double()
     assert grads["x"][2].abs().max().item() == 0.0
     for k, ref in tot.items():
-        e = rel_err(grads[k], ref)
-        print(f"bf16 training grad {k}: {e:.3e}")
-        assert e <= TOL_BF16, f"{k}: {e:.3e}"
+        ours, theirs = rel_err(grads[k], ref), rel_err(tot_ac[k], ref)
+        print(f"bf16 training grad {k}: ours vs fp64 {ours:.3e}; PyG-autocast vs fp64 {theirs:.3e}")
+        assert ours <= max(TOL_BF16, 1.25 * theirs), f"{k}: {ours:.3e} (PyG-autocast itself: {theirs:.3e})"
 
 
 def test_unpinned_gradient_report(cuda_device):
