@@ -66,7 +66,8 @@ int tecgat_plan_create(const int64_t *edge_index_dev, int64_t num_edges, int32_t
 int tecgat_plan_destroy(tecgat_plan_t *plan);
 /* info[0]=E (kept edges + N self loops) [1]=max in-degree [2]=max out-degree [3]=forward tiles
  * [4]=tile_nodes_fwd [5]=max forward window rows [6]=num_nodes [7]=kept (non-self) edges
- * [8]=backward tiles [9]=tile_nodes_bwd [10]=max backward window rows [11]=0 */
+ * [8]=backward tiles [9]=tile_nodes_bwd [10]=max backward window rows
+ * [11]=1 when the graph is banded and the sliding-window backward tiling was built (edge_bwd_sw.cu) */
 int tecgat_plan_info(const tecgat_plan_t *plan, int64_t *info12_host);
 /* Host copies for tests: rowptr (N+1), col (E) = source node of CSR slot k, eid (E) = index of that
  * edge in PyG's post-surgery edge order (kept edges in input order, then self loops).  Every CSR row

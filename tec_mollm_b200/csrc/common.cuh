@@ -76,6 +76,24 @@ struct tg_tiling {
     std::vector<int64_t> h_slab_off;  // (tiles + 1)
 };
 
+// Sliding-window backward tiling (edge_bwd_sw.cu): chunks of T consecutive nodes whose in- and out-neighbours all lie within
+// R rows (banded graph).  Two slabs per chunk, both with compile-time-free uniform sizes (plan-wide ELL row counts):
+//   slabD (destination role): int32 hdr[4] = {wlo, whi, 0, 0}; int32 k0[T] (first in-CSR slot: dropout counters);
+//         int32 deg[T] (in-degree | out-degree << 16, self loop included); uint16 ell_in[kinp][T]: window-relative row
+//         (col - wlo) of in-slot k = 1 + row (self loop excluded), padding = the node's own row
+//   slabS (source role): uint16 ell_out[koutp][T]: window-relative row of out-slot k (self loop included, k = 0);
+//         uint16 st_out[koutp][T]: stash address of that edge's (alpha q, d e) pair relative to the window start, in 8-byte
+//         units = u_rel * (stash_stride / 8) + in_slot * 2; padding = a slot the destination role zero-fills
+// window of chunk c: [wlo, whi) = [max(0, cT - R), min(N, (c+1)T + R))
+struct tg_sw_plan {
+    int32_t T = 0, J = 0, R = 0;
+    int32_t kin = 0, kout = 0;      // max in- / out-degree, self loop included
+    int32_t kinp = 0, koutp = 0;    // ELL rows: in (self excluded), out (self included), both padded to even counts
+    int32_t stash_stride = 0;       // bytes per node of the (alpha q, d e) stash: kin entries of 16 B + 8 B (bank spread)
+    int32_t slabD_bytes = 0, slabS_bytes = 0;
+    unsigned char *slabD = nullptr, *slabS = nullptr;  // device: J slabs each
+};
+
 struct tecgat_plan {
     int32_t num_nodes = 0;
     int64_t num_edges = 0;   // kept edges + N self loops

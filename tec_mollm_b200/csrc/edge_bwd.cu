@@ -47,44 +47,6 @@ struct EdgeBwdArgs {
     int64_t items;
 };
 
-constexpr int kBarConsumers = 1;  // named barrier id used by the consumer warps
-constexpr int kFlushItems = 256;   // items between two flushes of the per-lane fp32 parameter-gradient sums
-
-__device__ __forceinline__ void bar_sync_named(int id, int threads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
-
-// sgn-weighted accumulate:  B[c] += de * [s[c] > 0]
-template <int C>
-__device__ __forceinline__ void acc_step(CV<C> &B, const CV<C> &s, float de) {
-    const float2 de2 = splat(de);
-#pragma unroll
-    for (int i = 0; i < CV<C>::NP; ++i) {
-        const float2 step = make_float2(s.p[i].x > 0.f ? 1.f : 0.f, s.p[i].y > 0.f ? 1.f : 0.f);
-        B.p[i] = __ffma2_rn(de2, step, B.p[i]);
-    }
-    if (CV<C>::ODD) B.s = fmaf(de, s.s > 0.f ? 1.f : 0.f, B.s);
-}
-template <int C>
-__device__ __forceinline__ void cv_axpy(CV<C> &y, float a, const CV<C> &x) {
-    const float2 a2 = splat(a);
-#pragma unroll
-    for (int i = 0; i < CV<C>::NP; ++i) y.p[i] = __ffma2_rn(a2, x.p[i], y.p[i]);
-    if (CV<C>::ODD) y.s = fmaf(a, x.s, y.s);
-}
-
-template <bool DROP>  // DROP = false: inference / p = 0 instantiation without the hash
-struct DropCfg {
-    uint32_t thr, key;
-    float inv_keep;
-    __device__ __forceinline__ float q(uint32_t slot) const { return qh(slot * kDropMul + key); }
-    __device__ __forceinline__ float qh(uint32_t h) const {  // h = slot * kDropMul + key (consecutive slots: one add)
-        if (!DROP) return 1.f;
-        // no branch on "dropout off": threshold 0 keeps every edge and inv_keep is 1 (the loop bodies stay one basic block)
-        return dropout_finish(h) >= thr ? inv_keep : 0.f;
-    }
-};
-
 // score of an out-edge (v -> u) from the source's side:  c1 + att_m . |xl_v + xr_u|   (c1 = att_p . xl_v)
 template <int C>
 __device__ __forceinline__ float out_score(const CV<C> &attm, float c1, const CV<C> &xl_v, const CV<C> &xru, CV<C> &s) {
@@ -835,6 +797,19 @@ int tg::edge_bwd_run(const tecgat_plan_t *plan, const void *xl, const void *xr, 
     a.max_flushes = bwd_max_flushes(plan, snapshots);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int rc = TECGAT_ENOSUP;
+    {   // banded graphs at the reference's shapes: the sliding-window kernel (every edge's score evaluated once)
+        bool used = false;
+        rc = edge_bwd_sw_try(plan, xl, xr, att, bias, y, stat, gy, dxl, dxr, a.partials, grid, a.max_flushes, snapshots, heads, out_channels,
+                             negative_slope, dropout_p, a.drop_thr, seed, seed_dev, mode, dtype, st, &used);
+        if (rc != TECGAT_OK) return rc;
+        if (used) {
+            if (partial_rows) *partial_rows = int64_t(grid) * a.max_flushes;
+            if (!reduce) return TECGAT_OK;
+            ReduceSegs segs = {{datt, dbias, nullptr, nullptr}, {0, HC, 0, 0}, {HC, 2 * HC, 0, 0}};
+            return reduce_columns(a.partials, int64_t(grid) * a.max_flushes, 2 * HC, segs, st);
+        }
+        rc = TECGAT_ENOSUP;
+    }
 #define TG_CASE(CC)                                                                                                          \
     case CC:                                                                                                                 \
         if (vec) rc = dtype == TECGAT_F32 ? launch_bwd<CC, float, true>(a, plan, grid, st) : launch_bwd<CC, __nv_bfloat16, true>(a, plan, grid, st); \

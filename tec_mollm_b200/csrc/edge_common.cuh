@@ -237,6 +237,45 @@ __host__ __device__ __forceinline__ int row_period(uint32_t RB) {  // rows after
     return per;
 }
 
+// ---- pieces shared by the two backward kernels (edge_bwd.cu, edge_bwd_sw.cu) ---------------------------------------------
+constexpr int kBarConsumers = 1;  // named barrier id used by the consumer warps
+constexpr int kFlushItems = 256;   // items between two flushes of the per-lane fp32 parameter-gradient sums
+
+__device__ __forceinline__ void bar_sync_named(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// sgn-weighted accumulate:  B[c] += de * [s[c] > 0]
+template <int C>
+__device__ __forceinline__ void acc_step(CV<C> &B, const CV<C> &s, float de) {
+    const float2 de2 = splat(de);
+#pragma unroll
+    for (int i = 0; i < CV<C>::NP; ++i) {
+        const float2 step = make_float2(s.p[i].x > 0.f ? 1.f : 0.f, s.p[i].y > 0.f ? 1.f : 0.f);
+        B.p[i] = __ffma2_rn(de2, step, B.p[i]);
+    }
+    if (CV<C>::ODD) B.s = fmaf(de, s.s > 0.f ? 1.f : 0.f, B.s);
+}
+template <int C>
+__device__ __forceinline__ void cv_axpy(CV<C> &y, float a, const CV<C> &x) {
+    const float2 a2 = splat(a);
+#pragma unroll
+    for (int i = 0; i < CV<C>::NP; ++i) y.p[i] = __ffma2_rn(a2, x.p[i], y.p[i]);
+    if (CV<C>::ODD) y.s = fmaf(a, x.s, y.s);
+}
+
+template <bool DROP>  // DROP = false: inference / p = 0 instantiation without the hash
+struct DropCfg {
+    uint32_t thr, key;
+    float inv_keep;
+    __device__ __forceinline__ float q(uint32_t slot) const { return qh(slot * kDropMul + key); }
+    __device__ __forceinline__ float qh(uint32_t h) const {  // h = slot * kDropMul + key (consecutive slots: one add)
+        if (!DROP) return 1.f;
+        // no branch on "dropout off": threshold 0 keeps every edge and inv_keep is 1 (the loop bodies stay one basic block)
+        return dropout_finish(h) >= thr ? inv_keep : 0.f;
+    }
+};
+
 // internal entry points behind the C ABI (seed_dev != NULL: the dropout seed is read from device memory)
 int edge_fwd_run(const tecgat_plan_t *plan, const void *xl, const void *xr, const float *att, const float *bias, float *y,
                  float *stat, int32_t snapshots, int32_t heads, int32_t out_channels, float negative_slope, float dropout_p,
@@ -247,5 +286,11 @@ int edge_bwd_run(const tecgat_plan_t *plan, const void *xl, const void *xr, cons
                  const float *stat, const float *gy, void *dxl, void *dxr, float *datt, float *dbias, void *workspace,
                  int32_t snapshots, int32_t heads, int32_t out_channels, float negative_slope, float dropout_p, uint64_t seed,
                  const uint64_t *seed_dev, int32_t mode, int32_t dtype, void *stream, bool reduce, int64_t *partial_rows);
+
+// sliding-window backward (edge_bwd_sw.cu): *used = false (and TECGAT_OK) when the plan / shape does not qualify
+int edge_bwd_sw_try(const tecgat_plan_t *plan, const void *xl, const void *xr, const float *att, const float *bias, const float *y,
+                    const float *stat, const float *gy, void *dxl, void *dxr, float *partials, int grid, int max_flushes,
+                    int32_t snapshots, int32_t heads, int32_t out_channels, float negative_slope, float dropout_p, uint32_t drop_thr,
+                    uint64_t seed, const uint64_t *seed_dev, int32_t mode, int32_t dtype, cudaStream_t st, bool *used);
 
 }  // namespace tg

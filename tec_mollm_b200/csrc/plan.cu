@@ -94,6 +94,11 @@ extern "C" int tecgat_plan_destroy(tecgat_plan_t *p) {
     cudaFree(p->slot_out);
     free_tiling(p->fwd);
     free_tiling(p->bwd);
+    if (p->sw) {
+        cudaFree(p->sw->slabD);
+        cudaFree(p->sw->slabS);
+        delete p->sw;
+    }
     free(p->h_rowptr_in);
     free(p->h_col_in);
     free(p->h_eid_in);
@@ -176,6 +181,93 @@ static int build_tiling(tg_tiling &tl, bool bwd, int32_t T, int64_t N, const std
     if ((rc = upload(&tl.meta, tl.h_meta, st)) || (rc = upload(&tl.slabs, slabs, st)))
         return rc;
     TG_CUDA(cudaStreamSynchronize(st));  // `slabs` is a local
+    return TECGAT_OK;
+}
+
+// Sliding-window backward tiling (tg_sw_plan in common.cuh).  Returns with plan->sw == nullptr (and no error) when the graph
+// does not qualify: an edge longer than T rows, degrees beyond the slab limits, or a padding entry with no zero stash slot.
+static int build_sw(tecgat_plan_t *p, int32_t T, int64_t N, const std::vector<int32_t> &rp_in, const std::vector<int32_t> &col_in,
+                    const std::vector<int32_t> &rp_out, const std::vector<int32_t> &col_out, const std::vector<int32_t> &slot_out,
+                    cudaStream_t st) {
+    p->sw = nullptr;
+    if (T < 8 || (T % 8) != 0) return TECGAT_OK;
+    int32_t R = 0, kin = 0, kout = 0;
+    for (int64_t n = 0; n < N; ++n) {
+        kin = std::max(kin, rp_in[n + 1] - rp_in[n]);
+        kout = std::max(kout, rp_out[n + 1] - rp_out[n]);
+        for (int32_t k = rp_in[n]; k < rp_in[n + 1]; ++k) R = std::max<int32_t>(R, std::abs(col_in[k] - int32_t(n)));
+    }
+    if (R > T || kin > 48 || kout > 48) return TECGAT_OK;
+    tg_sw_plan *sw = new (std::nothrow) tg_sw_plan();
+    TG_REQUIRE(sw != nullptr, TECGAT_ENOMEM, "plan_create: out of host memory");
+    sw->T = T;
+    sw->J = int32_t((N + T - 1) / T);
+    sw->R = R;
+    sw->kin = kin;
+    sw->kout = kout;
+    sw->kinp = std::max(2, kin & ~1);  // kin - 1 in-slots besides the self loop, rounded up to an even count
+    sw->koutp = std::max(2, (kout + 1) & ~1);
+    // stash row of a node: slots 0 .. kinp (slot kinp is the one the destination role zero-fills whenever it is not a real
+    // edge) + 8 bytes so that consecutive nodes spread over the shared-memory banks (stride = 2 mod 4 words)
+    sw->stash_stride = (sw->kinp + 1) * 16 + 8;
+    const int32_t su = sw->stash_stride / 8;  // stash units (8 B) per node
+    sw->slabD_bytes = int32_t((16 + 8 * T + 2 * T * sw->kinp + 15) & ~15);
+    sw->slabS_bytes = int32_t((2 * T + 4 * T * sw->koutp + 15) & ~15);
+    std::vector<unsigned char> sd(size_t(sw->J) * sw->slabD_bytes, 0), ss(size_t(sw->J) * sw->slabS_bytes, 0);
+    bool ok = (int64_t(T) + 2 * R) * su <= 65535;
+    for (int32_t c = 0; c < sw->J && ok; ++c) {
+        const int64_t n0 = int64_t(c) * T, n1 = std::min<int64_t>(N, n0 + T);
+        const int32_t wlo = int32_t(std::max<int64_t>(0, n0 - R)), whi = int32_t(std::min<int64_t>(N, n0 + T + R));
+        int32_t *hdr = reinterpret_cast<int32_t *>(sd.data() + size_t(c) * sw->slabD_bytes);
+        int32_t *k0 = hdr + 4, *deg = k0 + T;
+        uint16_t *ell_in = reinterpret_cast<uint16_t *>(deg + T);
+        uint16_t *dego = reinterpret_cast<uint16_t *>(ss.data() + size_t(c) * sw->slabS_bytes);  // out-degree per node
+        uint16_t *ell_out = dego + T;
+        uint16_t *st_out = ell_out + size_t(sw->koutp) * T;
+        hdr[0] = wlo;
+        hdr[1] = whi;
+        // a stash slot that is zero for sure: slot kinp of any window node whose in-degree does not reach it
+        int32_t zero_node = -1;
+        for (int32_t u = wlo; u < whi && zero_node < 0; ++u)
+            if (rp_in[u + 1] - rp_in[u] <= sw->kinp) zero_node = u;
+        for (int64_t n = n0; n < n1; ++n) {
+            const int32_t i = int32_t(n - n0), di = rp_in[n + 1] - rp_in[n], dout = rp_out[n + 1] - rp_out[n];
+            k0[i] = rp_in[n];
+            deg[i] = di | (dout << 16);
+            dego[i] = uint16_t(dout);
+            for (int32_t k = 1; k <= sw->kinp; ++k)
+                ell_in[size_t(k - 1) * T + i] = uint16_t((k < di ? col_in[rp_in[n] + k] : int32_t(n)) - wlo);
+            const int32_t own_zero = di <= sw->kinp ? int32_t(n) : zero_node;
+            for (int32_t k = 0; k < sw->koutp; ++k) {
+                if (k < dout) {
+                    const int32_t u = col_out[rp_out[n] + k], slot = slot_out[rp_out[n] + k] - rp_in[u];  // in-slot of the edge at u
+                    ell_out[size_t(k) * T + i] = uint16_t(u - wlo);
+                    st_out[size_t(k) * T + i] = uint16_t((u - wlo) * su + slot * 2);
+                } else {
+                    if (own_zero < 0) { ok = false; break; }
+                    ell_out[size_t(k) * T + i] = uint16_t(own_zero - wlo);  // a valid row; its contribution is multiplied by zero
+                    st_out[size_t(k) * T + i] = uint16_t((own_zero - wlo) * su + sw->kinp * 2);
+                }
+            }
+        }
+        for (int64_t i = n1 - n0; i < T; ++i) {  // padding nodes of the last chunk: degree 0, entries point at the window start
+            k0[i] = 0;
+            deg[i] = 0;
+        }
+    }
+    if (!ok) {
+        delete sw;
+        return TECGAT_OK;
+    }
+    int rc;
+    if ((rc = upload(&sw->slabD, sd, st)) || (rc = upload(&sw->slabS, ss, st))) {
+        cudaFree(sw->slabD);
+        cudaFree(sw->slabS);
+        delete sw;
+        return rc;
+    }
+    TG_CUDA(cudaStreamSynchronize(st));  // the uploads read locals
+    p->sw = sw;
     return TECGAT_OK;
 }
 
@@ -271,7 +363,8 @@ extern "C" int tecgat_plan_create(const int64_t *edge_index_dev, int64_t num_edg
         (rc = upload(&p->rowptr_out, rp_out, st)) || (rc = upload(&p->col_out, col_out, st)) ||
         (rc = upload(&p->slot_out, slot_out, st)) ||
         (rc = build_tiling(p->fwd, false, tile_nodes_fwd, N, rp_in, col_in, rp_out, col_out, slot_out, st)) ||
-        (rc = build_tiling(p->bwd, true, tile_nodes_bwd, N, rp_in, col_in, rp_out, col_out, slot_out, st))) {
+        (rc = build_tiling(p->bwd, true, tile_nodes_bwd, N, rp_in, col_in, rp_out, col_out, slot_out, st)) ||
+        (rc = build_sw(p, tile_nodes_bwd, N, rp_in, col_in, rp_out, col_out, slot_out, st))) {
         tecgat_plan_destroy(p);
         return rc;
     }
@@ -310,7 +403,7 @@ extern "C" int tecgat_plan_info(const tecgat_plan_t *p, int64_t *info) {
     info[8] = p->bwd.num_tiles;
     info[9] = p->bwd.T;
     info[10] = p->bwd.max_window;
-    info[11] = 0;
+    info[11] = p->sw ? 1 : 0;  // the sliding-window backward tiling exists (banded graph)
     return TECGAT_OK;
 }
 

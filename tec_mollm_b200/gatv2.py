@@ -82,7 +82,8 @@ class GraphPlan:
         info = (C.c_int64 * 12)()
         _lib.call("tecgat_plan_info", self._h, info)
         (self.num_edges, self.max_in_degree, self.max_out_degree, self.num_tiles, _, self.max_window, _,
-         self.kept_edges, self.num_tiles_bwd, _, self.max_window_bwd, _) = [int(v) for v in info]
+         self.kept_edges, self.num_tiles_bwd, _, self.max_window_bwd, sw) = [int(v) for v in info]
+        self.sliding_window = bool(sw)  # banded graph: the backward can run the sliding-window kernel
 
     @property
     def handle(self):
