@@ -29,6 +29,10 @@ NVCC_FLAGS = [
 ]
 
 
+# experiment switches (e.g. TECGAT_NVCC_EXTRA="-DTG_SW_FAKE_OWN"): part of the digest, so a plain build afterwards rebuilds
+EXTRA = os.environ.get("TECGAT_NVCC_EXTRA", "").split()
+
+
 def _nvcc() -> str:
     exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(exe):
@@ -40,7 +44,7 @@ def _digest(paths) -> str:
     """Content hash of the sources (mtimes do not survive the snapshot to the GPU box)."""
     import hashlib
 
-    h = hashlib.sha256(" ".join(NVCC_FLAGS[:8]).encode())
+    h = hashlib.sha256(" ".join(NVCC_FLAGS[:8] + EXTRA).encode())
     for p in sorted(paths):
         h.update(os.path.basename(p).encode())
         with open(p, "rb") as f:
@@ -67,7 +71,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         ostamp, owant = obj + ".sha256", _digest([src] + headers)
         if not force and os.path.exists(obj) and os.path.exists(ostamp) and open(ostamp).read().strip() == owant:
             return obj
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + EXTRA + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")

@@ -125,6 +125,10 @@ struct tecgat_plan {
 // ------------------------------------------------------------------------------------------------
 #if defined(__CUDACC__)
 
+#ifndef TG_PRODUCER_SLEEP_NS
+#define TG_PRODUCER_SLEEP_NS 400
+#endif
+
 namespace tg {
 
 constexpr int kSmemBudget = 200 * 1024;  // per-CTA dynamic shared memory we are willing to request
@@ -182,6 +186,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     }
 }
 
+// Producer-side wait: the producer warp runs a whole item ahead of the consumers, so wake-up latency is irrelevant; sleeping
+// between polls leaves the issue slots of its scheduler to the two consumer warps it shares it with (try_wait's own suspend
+// hint returns within ~20 ns: a bare poll loop issues ~5 instructions every ~40 cycles).
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    uint32_t polls = 0;
+    long long t0 = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(TG_PRODUCER_SLEEP_NS);
+        if ((++polls & 255u) == 0u) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000LL) {
+                printf("tecgat: producer mbarrier wait timed out (block %d thread %d parity %u)\n", (int)blockIdx.x, (int)threadIdx.x, parity);
+                __trap();
+            }
+        }
+    }
+}
+
 // ---- bulk TMA (cp.async.bulk): 1-D, 16-byte aligned, size a multiple of 16 ------------------
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -199,6 +223,10 @@ __device__ __forceinline__ void bulk_s2g_add_f32(void *dst_gmem, const void *src
     asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst_gmem),
                  "r"(smem_u32(src_smem)), "r"(bytes)
                  : "memory");
+}
+// L2 prefetch of a contiguous global range (16-byte aligned, size a multiple of 16): no destination, no completion
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src_gmem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }

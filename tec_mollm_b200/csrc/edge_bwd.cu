@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(WG ? 384 : 256, 1) edge_bwd_kernel(const EdgeB
                 unsigned char *stage = smem + a.off_stage0 + (size_t)ring.st * a.stage_bytes;
                 const WinCopy c3 = win_copy(a.stat, row0, win, RB_STAT, a.per_stat, Rtot);
                 if (SEMI) {  // slab + stat window only; the consumers gather xl / xr / g / y rows from global memory (L2)
-                    if (lane == 0) mbar_wait(&empty[ring.st], ring.ph ^ 1u);
+                    if (lane == 0) mbar_wait_relaxed(&empty[ring.st], ring.ph ^ 1u);
                     __syncwarp();
                     if (c3.tail) {
                         win_copy_tail(c3, stage + a.off_statraw, lane);
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(WG ? 384 : 256, 1) edge_bwd_kernel(const EdgeB
                     const WinCopy c0 = win_copy(a.xl, row0, win, RB_ST, a.per_st, Rtot);
                     const WinCopy c1 = win_copy(a.xr, row0, win, RB_ST, a.per_st, Rtot);
                     const WinCopy c2 = win_copy(a.gy, row0, win, RB_F, a.per_f, Rtot);
-                    if (lane == 0) mbar_wait(&empty[ring.st], ring.ph ^ 1u);
+                    if (lane == 0) mbar_wait_relaxed(&empty[ring.st], ring.ph ^ 1u);
                     __syncwarp();
                     if (c0.tail | c1.tail | c2.tail | c3.tail) {  // only the last rows of the last snapshot
                         win_copy_tail(c0, stage + a.off_xl, lane);
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(WG ? 384 : 256, 1) edge_bwd_kernel(const EdgeB
                 }
                 if (do_y) {
                     const WinCopy c4 = win_copy(a.y, row0, win, RB_F, a.per_f, Rtot);
-                    if (lane == 0) mbar_wait(yempty, yph ^ 1u);  // the single y window: released right after the delta pre-pass
+                    if (lane == 0) mbar_wait_relaxed(yempty, yph ^ 1u);  // the single y window: released right after the delta pre-pass
                     __syncwarp();
                     if (c4.tail) {
                         win_copy_tail(c4, smem + a.off_y, lane);

@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(512, 1) edge_fwd_kernel(const EdgeFwdArgs a) {
                 unsigned char *stage = smem + a.off_stage0 + (size_t)ring.st * a.stage_bytes;
                 const WinCopy cr = win_copy(a.xr, (int64_t)snap * N + n0, nt, RB, a.per, Rtot);
                 const WinCopy cl = win_copy(a.xl, (int64_t)snap * N + lo, win, RB, a.per, Rtot);
-                if (lane == 0) mbar_wait(&empty[ring.st], ring.ph ^ 1u);
+                if (lane == 0) mbar_wait_relaxed(&empty[ring.st], ring.ph ^ 1u);
                 __syncwarp();
                 if (cr.tail | cl.tail) {  // only the last rows of the last snapshot
                     win_copy_tail(cr, stage + a.off_xr, lane);
