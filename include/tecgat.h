@@ -194,6 +194,23 @@ int tecgat_embed_bwd(const float *ge_dev, const int32_t *tf_dev, float *dnode_de
                      int32_t snapshots, int32_t nodes, int32_t raw_channels, int32_t emb_dim, int32_t n_tod,
                      int32_t n_doy, int32_t n_year, int32_t n_season, int32_t accumulate, void *stream);
 
+/* ---- TemporalEncoder, the part between the convolutions of a Multi_Scale_Conv_Block (src/model/modules.py:13-60; SURVEY.md
+ *      8f N3): replaces, per branch k = 3 / 5 / 7, GroupNorm(1, C) (:26) + GELU (:27), the channel concat (:52) and the strided
+ *      read of the 1x1 convolution (:36-41, :55) with one pass.  y: (samples, branches*C, L) -- the three branch convolutions'
+ *      outputs in concatenated channel order; z: (samples, branches*C, ceil(L / stride)) = only the positions the strided 1x1
+ *      convolution reads, already normalised, affine-mapped (gamma, beta: (branches, C)) and passed through the exact GELU.
+ *      mean / rstd: (samples, branches) saved for backward.  Backward: d y from d z (GELU', affine, GroupNorm Jacobian) and
+ *      d gamma / d beta by fixed-order two-stage sums (no atomics).  dtypes: TECGAT_F32 / TECGAT_BF16 for y (and d y) and for
+ *      z (and d z); arithmetic in fp32.  channels * L <= 8192. */
+int tecgat_gn_gelu_fwd(const void *y_dev, const float *gamma_dev, const float *beta_dev, void *z_dev,
+                       float *mean_dev, float *rstd_dev, int64_t samples, int32_t branches, int32_t channels,
+                       int32_t length, int32_t stride, float eps, int32_t y_dtype, int32_t z_dtype, void *stream);
+int64_t tecgat_gn_gelu_bwd_workspace(int64_t samples, int32_t branches, int32_t channels);
+int tecgat_gn_gelu_bwd(const void *y_dev, const float *gamma_dev, const float *beta_dev, const float *mean_dev,
+                       const float *rstd_dev, const void *dz_dev, void *dy_dev, float *dgamma_dev,
+                       float *dbeta_dev, void *workspace_dev, int64_t samples, int32_t branches, int32_t channels,
+                       int32_t length, int32_t stride, int32_t y_dtype, int32_t z_dtype, void *stream);
+
 /* ---- graph builder: replaces calculate_haversine_distance_matrix (src/graph/graph_constructor.py:34-59,
  *      sklearn haversine_distances in fp64), construct_binary_adjacency (:61-81, inclusive `<=`, zero
  *      diagonal), symmetrically_normalize_adjacency (:99-128) and the COO extraction of

@@ -4,7 +4,8 @@ computed by the hand-written CUDA library ``lib/libtecgat.so`` behind the C ABI 
 from .gatv2 import GATv2Conv, GraphPlan, tile_nodes_for  # noqa: F401
 from .spatial_encoder import SpatialEncoder  # noqa: F401
 from .embedding import SpatioTemporalEmbedding  # noqa: F401
+from .temporal import MultiScaleConvEmbedder, Multi_Scale_Conv_Block  # noqa: F401
 from . import graph  # noqa: F401
 from . import dist  # noqa: F401
 
-__all__ = ["GATv2Conv", "GraphPlan", "SpatialEncoder", "SpatioTemporalEmbedding", "graph", "dist", "tile_nodes_for"]
+__all__ = ["GATv2Conv", "GraphPlan", "SpatialEncoder", "SpatioTemporalEmbedding", "Multi_Scale_Conv_Block", "MultiScaleConvEmbedder", "graph", "dist", "tile_nodes_for"]

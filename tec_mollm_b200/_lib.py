@@ -51,6 +51,9 @@ _SIGNATURES = {
     "tecgat_embed_fwd": (C.c_int, [_vp] * 8 + [_i32] * 8 + [_vp]),
     "tecgat_embed_bwd_workspace": (_i64, [_i32, _i32, _i32]),
     "tecgat_embed_bwd": (C.c_int, [_vp] * 8 + [_i32] * 9 + [_vp]),
+    "tecgat_gn_gelu_fwd": (C.c_int, [_vp] * 6 + [_i64, _i32, _i32, _i32, _i32, _f32, _i32, _i32, _vp]),
+    "tecgat_gn_gelu_bwd_workspace": (_i64, [_i64, _i32, _i32]),
+    "tecgat_gn_gelu_bwd": (C.c_int, [_vp] * 10 + [_i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "tecgat_residual_permute_fwd": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "tecgat_residual_permute_bwd": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "tecgat_dropout_mask_host": (C.c_int, [_u64, _i64, _i64, _i32, _f32, _i64, _vp]),
