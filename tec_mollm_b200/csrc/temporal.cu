@@ -155,7 +155,7 @@ static GnParams gn_params(const float *gamma, const float *beta, int branches, i
     return GnParams{gamma, beta, branches, (uint32_t)(4294967296ull / (uint64_t)L) + 1u, (uint32_t)(4294967296ull / (uint64_t)Lo) + 1u};
 }
 static int gn_bwd_grid(int64_t samples, int branches) {
-    const int64_t per_branch = std::min<int64_t>(samples, std::max(1, 4 * tg_sm_count() / branches));
+    const int64_t per_branch = std::min<int64_t>(samples, std::max(1, 8 * tg_sm_count() / branches));
     return (int)(per_branch * branches);
 }
 

@@ -61,13 +61,15 @@ class LoRA(nn.Module):  # y = base(x) + (x A) B * (alpha / r) around GPT-2's Con
 
 
 class StandIn(nn.Module):
-    def __init__(self, fused: bool):
+    def __init__(self, fused: bool, temporal: str = "torch"):
         super().__init__()
         from transformers import GPT2Config, GPT2Model
+        from tec_mollm_b200 import MultiScaleConvEmbedder
         self.fused = fused
         self.spatio_temporal_embedding = SpatioTemporalEmbedding(16, num_nodes=N)     # tec_mollm.py:25-29 (drop-in)
         self.spatial_encoder = SpatialEncoder(22, 11, heads=2, snapshot_mode="shared")  # tec_mollm.py:33-37 (drop-in)
-        self.temporal = nn.Sequential(MSBlock(22, 64), MSBlock(64, 128))
+        # TemporalEncoder conv embedder (modules.py:62-91): plain torch ops, or this repository's drop-in
+        self.temporal = MultiScaleConvEmbedder(22, [64, 128], [2, 2]) if temporal == "fused" else nn.Sequential(MSBlock(22, 64), MSBlock(64, 128))
         self.patch = nn.Linear(128 * 4, D_LLM)
         self.llm = GPT2Model(GPT2Config(n_layer=3, n_positions=64))
         for p in self.llm.parameters():
@@ -91,9 +93,9 @@ class StandIn(nn.Module):
         return self.head(h.reshape(B * N, -1)).view(B, N, L_OUT).permute(0, 2, 1).unsqueeze(-1)
 
 
-def run(fused, hygiene, accum, opt_steps, ddp, dev, rank, world):
+def run(fused, hygiene, accum, opt_steps, ddp, dev, rank, world, temporal="torch"):
     torch.manual_seed(0)
-    model = StandIn(fused).to(dev).train()
+    model = StandIn(fused, temporal).to(dev).train()
     net = nn.parallel.DistributedDataParallel(model, device_ids=[dev.index]) if ddp else model   # train.py:354
     lat, lon = np.linspace(15, 55, 41), np.linspace(70, 140, 71)
     ei, _ = graph.build_graph(lat, lon, 150.0, device=dev)
@@ -176,7 +178,8 @@ def run(fused, hygiene, accum, opt_steps, ddp, dev, rank, world):
     torch.cuda.synchronize(dev)
     ms_block = e0.elapsed_time(e1) / 20
     return {"what": "config2_train_loop_stand_in", "hygiene": hygiene, "ddp_world": world if ddp else 1, "batch_per_gpu": B,
-            "accumulation_steps": accum, "spatial_block": "fused embedding + forward_block" if fused else "fused embedding + reference glue (torch ops)",
+            "accumulation_steps": accum, "temporal_conv_embedder": "tec_mollm_b200.MultiScaleConvEmbedder" if temporal == "fused" else "torch ops",
+            "spatial_block": "fused embedding + forward_block" if fused else "fused embedding + reference glue (torch ops)",
             "ms_per_optimizer_step": ms, "ms_per_micro_step": ms / accum, "samples_per_s": world * B * accum / (ms * 1e-3),
             "ms_spatial_block_fwd_bwd": ms_block, "spatial_share_of_micro_step": ms_block / (ms / accum),
             "note": "bf16 autocast, eager; everything outside the spatial block is a plain-torch stand-in with the reference's shapes"}
@@ -191,11 +194,10 @@ def main():
     rank, world, local_rank = tdist.init_from_env("nccl") if args.ddp else (0, 1, 0)
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
-    for hygiene in ("reference", "clean"):
-        for fused in (False, True):
-            r = run(fused, hygiene, args.accum, args.opt_steps, args.ddp, dev, rank, world)
-            if rank == 0:
-                print(json.dumps(r), flush=True)
+    for hygiene, fused, temporal in (("reference", False, "torch"), ("clean", False, "torch"), ("clean", True, "torch"), ("clean", True, "fused")):
+        r = run(fused, hygiene, args.accum, args.opt_steps, args.ddp, dev, rank, world, temporal)
+        if rank == 0:
+            print(json.dumps(r), flush=True)
     if args.ddp:
         dist.barrier(device_ids=[local_rank])
         dist.destroy_process_group()
