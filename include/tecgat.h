@@ -217,10 +217,13 @@ int tecgat_gn_gelu_bwd(const void *y_dev, const float *gamma_dev, const float *b
  *      convert_to_pyg_and_save (:141-144).  Inputs are per-node coordinates in RADIANS (device, fp64).
  *
  *  tecgraph_distance_rows : dense rows D[r0:r1, 0:n] in km (fp64), for the dense-API mirror.
- *  tecgraph_edges_count   : pass 1 -- per-row neighbour counts (deg_dev, int32, n entries), total in
- *                           *total_host; pairs whose distance is within a relative guard band of the
- *                           threshold are re-evaluated on the host with the reference's exact libm
- *                           formula so the edge SET is bit-exact (synchronises the stream).
+ *  tecgraph_edges_count   : pass 1 -- per-row neighbour counts and their device-side scan, total in *total_host.
+ *                           One warp per row over 32-column chunks; a chunk is skipped when its latitude or
+ *                           longitude range alone puts it beyond the threshold; cos(lat) is evaluated once per
+ *                           node; "d <= thr" is decided on the haversine argument r against sin^2(thr / 2R)
+ *                           (no asin / sqrt per pair).  Pairs inside a relative guard band of the threshold
+ *                           are re-evaluated on the host with the reference's exact libm formula so the edge
+ *                           SET is bit-exact (synchronises the stream).
  *  tecgraph_edges_fill    : pass 2 -- edge_index (2, E) int64 row-major (row ascending, column ascending
  *                           inside a row, exactly scipy's COO order) and edge_weight fp32 =
  *                           fp32((1/sqrt(deg_r) * 1.0) * 1/sqrt(deg_c)).                              */
@@ -233,6 +236,9 @@ int tecgraph_edges_count(const double *lat_dev, const double *lon_dev, int64_t n
 int tecgraph_edges_fill(tecgraph_ctx_t *ctx, int64_t *edge_index_dev, float *edge_weight_dev,
                         void *stream);
 int tecgraph_ctx_destroy(tecgraph_ctx_t *ctx);
+/* stats4 = {count-kernel ms, fill-kernel ms (0 before tecgraph_edges_fill), pairs evaluated by the count pass, guard-band
+ * pairs re-checked on the host}: CUDA-event times of the two edge kernels (synchronises them). */
+int tecgraph_ctx_stats(tecgraph_ctx_t *ctx, double *stats4_host);
 
 #ifdef __cplusplus
 }

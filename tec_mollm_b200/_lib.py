@@ -61,6 +61,7 @@ _SIGNATURES = {
     "tecgraph_edges_count": (C.c_int, [_vp, _vp, _i64, _f64, _f64, _vp, C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_i64)]),
     "tecgraph_edges_fill": (C.c_int, [_vp, _vp, _vp, _vp]),
     "tecgraph_ctx_destroy": (C.c_int, [_vp]),
+    "tecgraph_ctx_stats": (C.c_int, [_vp, _vp]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

@@ -24,14 +24,20 @@
 
 struct tecgraph_ctx {
     int64_t n = 0;
-    double thr = 0, radius = 0;
+    double thr = 0, radius = 0, r_lo = 0, r_hi = 0;
+    unsigned char *slab = nullptr;          // ONE device allocation holding everything below
     double *lat = nullptr, *lon = nullptr;  // device copies (n)
-    double *cmin = nullptr, *cmax = nullptr;  // per 32-column chunk latitude range
-    int32_t *deg = nullptr;                 // (n) neighbour counts, ambiguous pairs resolved
-    int64_t *rowptr = nullptr;              // (n+1)
-    int64_t *extra = nullptr;               // sorted keys i*n+j of guard-band pairs that ARE edges (host verdict)
+    double *clat = nullptr;                 // cos(lat) per node: evaluated once, not once per pair
+    double *cmin = nullptr, *cmax = nullptr, *lmin = nullptr, *lmax = nullptr, *ccos = nullptr;  // per 32-column chunk
+    int32_t *deg = nullptr, *evals = nullptr;  // (n) neighbour counts (ambiguous pairs resolved), pairs evaluated
+    int64_t *rowptr = nullptr;              // (n+1), device-side scan
+    int64_t *amb = nullptr;                 // guard-band pair keys i*n+j
+    int64_t *totals = nullptr;              // {edges, evaluated pairs, guard-band pairs}
+    int64_t *extra = nullptr;               // sorted keys of guard-band pairs that ARE edges (host verdict)
     int64_t num_extra = 0;
-    int64_t total = 0;
+    int64_t total = 0, evaluated = 0, ambiguous = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // count kernel begin/end, fill kernel begin/end
+    bool filled = false;
 };
 
 namespace tg {
@@ -55,25 +61,41 @@ __global__ void distance_rows_kernel(const double *__restrict__ lat, const doubl
     if (j < n && i < r1) out[(i - r0) * n + j] = hav_km(lat[i], lon[i], lat[j], lon[j], radius);
 }
 
-__global__ void chunk_range_kernel(const double *__restrict__ lat, int64_t n, double *__restrict__ cmin,
-                                   double *__restrict__ cmax) {
+__global__ void node_cos_kernel(const double *__restrict__ lat, int64_t n, double *__restrict__ clat) {
+    const int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (j < n) clat[j] = cos(lat[j]);
+}
+
+__global__ void chunk_range_kernel(const double *__restrict__ lat, const double *__restrict__ lon, const double *__restrict__ clat,
+                                   int64_t n, double *__restrict__ cmin, double *__restrict__ cmax, double *__restrict__ lmin,
+                                   double *__restrict__ lmax, double *__restrict__ ccos) {
     const int64_t c = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     const int64_t nchunks = (n + 31) / 32;
     if (c >= nchunks) return;
-    double lo = INFINITY, hi = -INFINITY;
+    double lo = INFINITY, hi = -INFINITY, llo = INFINITY, lhi = -INFINITY, cc = INFINITY;
     for (int64_t j = c * 32; j < min(n, c * 32 + 32); ++j) {
         lo = fmin(lo, lat[j]);
         hi = fmax(hi, lat[j]);
+        llo = fmin(llo, lon[j]);
+        lhi = fmax(lhi, lon[j]);
+        cc = fmin(cc, clat[j]);
     }
-    cmin[c] = lo;
-    cmax[c] = hi;
+    cmin[c] = lo; cmax[c] = hi; lmin[c] = llo; lmax[c] = lhi;
+    ccos[c] = fmax(cc, 0.0);
 }
 
-// 0 = not an edge, 1 = edge, 2 = inside the guard band (host decides)
-__device__ __forceinline__ int classify(double d, double thr) {
-    const double band = thr * kGuard;
-    if (d > thr + band) return 0;
-    if (d < thr - band) return 1;
+// The reference's haversine argument in its operation order (sklearn: sin_0 * sin_0 + cos(lat1) * cos(lat2) * sin_1 * sin_1):
+//     r = sin^2((lat1 - lat2) / 2) + ((cos(lat1) cos(lat2)) sin((lon1 - lon2) / 2)) sin((lon1 - lon2) / 2)
+// d = 2 R asin(sqrt(r)) is monotone in r, so "d <= thr" is decided on r against r_thr = sin^2(thr / 2R) with a guard band:
+// no asin / sqrt per pair.  0 = not an edge, 1 = edge, 2 = inside the guard band (the host's libm decides on d itself).
+__device__ __forceinline__ int classify_pair(double lat_i, double lon_i, double clat_i, double lat_j, double lon_j, double clat_j,
+                                             double r_lo, double r_hi) {
+    const double s0 = sin(__dmul_rn(0.5, __dsub_rn(lat_i, lat_j)));
+    const double s1 = sin(__dmul_rn(0.5, __dsub_rn(lon_i, lon_j)));
+    const double cc = __dmul_rn(clat_i, clat_j);
+    const double r = __dadd_rn(__dmul_rn(s0, s0), __dmul_rn(__dmul_rn(cc, s1), s1));
+    if (r > r_hi) return 0;
+    if (r < r_lo) return 1;
     return 2;
 }
 
@@ -88,52 +110,76 @@ __device__ __forceinline__ bool extra_contains(const int64_t *__restrict__ extra
     return false;
 }
 
+struct EdgeArgs {
+    const double *lat, *lon, *clat, *cmin, *cmax, *lmin, *lmax, *ccos;
+    int64_t n;
+    double gap, r_lo, r_hi;
+    int32_t *deg, *evals;
+    int64_t *amb;
+    unsigned int *amb_count;
+    const int64_t *extra;
+    int64_t num_extra;
+    const int64_t *rowptr;
+    int64_t *edge_index;
+    float *edge_weight;
+    int64_t total;
+};
+
+// One warp per row i, lanes over 32-column chunks.  A chunk is skipped when no node of it can be within the threshold:
+// latitude gap alone (d >= R |dlat|), or the longitude gap at the most favourable latitudes of the pair
+// (r >= cos(lat_i) min_j cos(lat_j) sin^2(dlon_min / 2), dlon_min taken around the +-pi seam).  On lat-major grids that
+// leaves a few dozen candidates per row instead of N.
 // FILL == false: count certain edges per row, append guard-band pairs to `amb` (keys i*n+j).
 // FILL == true : write (row, col, weight) in column order; guard-band pairs are edges iff their key is in `extra`.
 template <bool FILL>
-__global__ void __launch_bounds__(256) edges_kernel(const double *__restrict__ lat, const double *__restrict__ lon, int64_t n,
-                                                    double thr, double radius, const double *__restrict__ cmin,
-                                                    const double *__restrict__ cmax, int32_t *__restrict__ deg,
-                                                    int64_t *__restrict__ amb, unsigned int *__restrict__ amb_count,
-                                                    const int64_t *__restrict__ extra, int64_t num_extra,
-                                                    const int64_t *__restrict__ rowptr, int64_t *__restrict__ edge_index,
-                                                    float *__restrict__ edge_weight, int64_t total) {
+__global__ void __launch_bounds__(256) edges_kernel(const EdgeArgs a) {
     const int lane = threadIdx.x & 31;
     const int64_t i = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+    const int64_t n = a.n;
     if (i >= n) return;
-    const double lat_i = lat[i], lon_i = lon[i];
-    const double gap = (thr * (1.0 + 2.0 * kGuard)) / radius;  // chunks farther than this in latitude hold no candidates
+    const double lat_i = a.lat[i], lon_i = a.lon[i], clat_i = a.clat[i];
     const int64_t nchunks = (n + 31) / 32;
-    int count = 0;
-    int64_t pos = FILL ? rowptr[i] : 0;
+    int count = 0, evals = 0;
+    int64_t pos = FILL ? a.rowptr[i] : 0;
     double wi = 0.0;
-    if (FILL) wi = deg[i] > 0 ? 1.0 / sqrt(static_cast<double>(deg[i])) : 0.0;
+    if (FILL) wi = a.deg[i] > 0 ? 1.0 / sqrt(static_cast<double>(a.deg[i])) : 0.0;
     for (int64_t cb = 0; cb < nchunks; cb += 32) {
         const int64_t c = cb + lane;
         bool cand = false;
-        if (c < nchunks) cand = !(cmin[c] - lat_i > gap || lat_i - cmax[c] > gap);
+        if (c < nchunks && !(a.cmin[c] - lat_i > a.gap || lat_i - a.cmax[c] > a.gap)) {
+            // distance from lon_i to the chunk's longitude interval, also across the seam
+            const double lo = a.lmin[c], hi = a.lmax[c];
+            const double two_pi = 6.283185307179586476925286766559;
+            auto gap_to = [&](double x) { return fmax(0.0, fmax(lo - x, x - hi)); };
+            const double dl = fmin(gap_to(lon_i), fmin(gap_to(lon_i + two_pi), gap_to(lon_i - two_pi)));
+            const double sh = sin(0.5 * fmin(dl, 3.14159265358979323846));
+            cand = !(clat_i * a.ccos[c] * sh * sh > a.r_hi * (1.0 + 1e-6));
+        }
         unsigned todo = __ballot_sync(0xffffffffu, cand);
         while (todo) {
             const int b = __ffs(todo) - 1;
             todo &= todo - 1;
             const int64_t j = (cb + b) * 32 + lane;
             int cls = 0;
-            if (j < n && j != i) cls = classify(hav_km(lat_i, lon_i, lat[j], lon[j], radius), thr);
+            if (j < n && j != i) {
+                cls = classify_pair(lat_i, lon_i, clat_i, a.lat[j], a.lon[j], a.clat[j], a.r_lo, a.r_hi);
+                ++evals;
+            }
             if (!FILL) {
                 count += (cls == 1);
                 if (cls == 2) {
-                    const unsigned slot = atomicAdd(amb_count, 1u);  // integer append; order is irrelevant (sorted on host)
-                    if (slot < (unsigned)kMaxAmbiguous) amb[slot] = i * n + j;
+                    const unsigned slot = atomicAdd(a.amb_count, 1u);  // integer append; order is irrelevant (sorted on host)
+                    if (slot < (unsigned)kMaxAmbiguous) a.amb[slot] = i * n + j;
                 }
             } else {
-                const bool is_edge = cls == 1 || (cls == 2 && extra_contains(extra, num_extra, i * n + j));
+                const bool is_edge = cls == 1 || (cls == 2 && extra_contains(a.extra, a.num_extra, i * n + j));
                 const unsigned mask = __ballot_sync(0xffffffffu, is_edge);
                 if (is_edge) {
                     const int64_t p = pos + __popc(mask & ((1u << lane) - 1u));
-                    edge_index[p] = i;
-                    edge_index[total + p] = j;
-                    const double wj = deg[j] > 0 ? 1.0 / sqrt(static_cast<double>(deg[j])) : 0.0;
-                    edge_weight[p] = static_cast<float>((wi * 1.0) * wj);
+                    a.edge_index[p] = i;
+                    a.edge_index[a.total + p] = j;
+                    const double wj = a.deg[j] > 0 ? 1.0 / sqrt(static_cast<double>(a.deg[j])) : 0.0;
+                    a.edge_weight[p] = static_cast<float>((wi * 1.0) * wj);
                 }
                 pos += __popc(mask);
             }
@@ -141,8 +187,48 @@ __global__ void __launch_bounds__(256) edges_kernel(const double *__restrict__ l
     }
     if (!FILL) {
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) count += __shfl_xor_sync(0xffffffffu, count, off);
-        if (lane == 0) deg[i] = count;
+        for (int off = 16; off > 0; off >>= 1) {
+            count += __shfl_xor_sync(0xffffffffu, count, off);
+            evals += __shfl_xor_sync(0xffffffffu, evals, off);
+        }
+        if (lane == 0) {
+            a.deg[i] = count;
+            a.evals[i] = evals;
+        }
+    }
+}
+
+// device-side exclusive scan of the degrees (one CTA: n is at most a few 10^5) + totals {edges, evaluated pairs}
+__global__ void __launch_bounds__(1024) scan_kernel(const int32_t *__restrict__ deg, const int32_t *__restrict__ evals, int64_t n,
+                                                    int64_t *__restrict__ rowptr, int64_t *__restrict__ totals) {
+    __shared__ int64_t part[1024], epart[1024];
+    const int t = threadIdx.x;
+    const int64_t per = (n + 1023) / 1024, b0 = min(n, t * per), b1 = min(n, b0 + per);
+    int64_t s = 0, e = 0;
+    for (int64_t i = b0; i < b1; ++i) {
+        s += deg[i];
+        e += evals ? evals[i] : 0;
+    }
+    part[t] = s;
+    epart[t] = e;
+    __syncthreads();
+    if (t == 0) {
+        int64_t run = 0, erun = 0;
+        for (int k = 0; k < 1024; ++k) {
+            const int64_t v = part[k];
+            part[k] = run;
+            run += v;
+            erun += epart[k];
+        }
+        rowptr[n] = run;
+        totals[0] = run;
+        if (evals) totals[1] = erun;
+    }
+    __syncthreads();
+    int64_t run = part[t];
+    for (int64_t i = b0; i < b1; ++i) {
+        rowptr[i] = run;
+        run += deg[i];
     }
 }
 
@@ -176,15 +262,24 @@ extern "C" int tecgraph_distance_rows(const double *lat, const double *lon, int6
 
 extern "C" int tecgraph_ctx_destroy(tecgraph_ctx_t *c) {
     if (!c) return TECGAT_OK;
-    cudaFree(c->lat);
-    cudaFree(c->lon);
-    cudaFree(c->cmin);
-    cudaFree(c->cmax);
-    cudaFree(c->deg);
-    cudaFree(c->rowptr);
+    cudaFree(c->slab);
     cudaFree(c->extra);
+    for (cudaEvent_t e : c->ev)
+        if (e) cudaEventDestroy(e);
     delete c;
     return TECGAT_OK;
+}
+
+static tg::EdgeArgs edge_args(const tecgraph_ctx_t *c) {
+    tg::EdgeArgs a;
+    a.lat = c->lat; a.lon = c->lon; a.clat = c->clat; a.cmin = c->cmin; a.cmax = c->cmax; a.lmin = c->lmin; a.lmax = c->lmax; a.ccos = c->ccos;
+    a.n = c->n;
+    a.gap = (c->thr * (1.0 + 2.0 * tg::kGuard)) / c->radius;  // chunks farther than this in latitude hold no candidates
+    a.r_lo = c->r_lo; a.r_hi = c->r_hi;
+    a.deg = c->deg; a.evals = c->evals; a.amb = c->amb; a.amb_count = reinterpret_cast<unsigned int *>(c->totals + 2);
+    a.extra = c->extra; a.num_extra = c->num_extra; a.rowptr = c->rowptr;
+    a.edge_index = nullptr; a.edge_weight = nullptr; a.total = c->total;
+    return a;
 }
 
 extern "C" int tecgraph_edges_count(const double *lat, const double *lon, int64_t n, double thr_km, double radius_km,
@@ -198,13 +293,14 @@ extern "C" int tecgraph_edges_count(const double *lat, const double *lon, int64_
     tecgraph_ctx_t *c = new (std::nothrow) tecgraph_ctx_t();
     TG_REQUIRE(c, TECGAT_ENOMEM, "edges_count: out of host memory");
     c->n = n; c->thr = thr_km; c->radius = radius_km;
+    {   // d <= thr  <=>  r <= sin^2(thr / 2R); a relative band of 4e-9 in r covers the 1e-9 band in d (d ~ 2R sqrt(r))
+        const double half = thr_km / (2.0 * radius_km);
+        const double rt = half >= 1.5707963267948966 ? 2.0 : sin(half) * sin(half);
+        c->r_lo = rt * (1.0 - 4.0 * kGuard);
+        c->r_hi = rt * (1.0 + 4.0 * kGuard);
+    }
     const int64_t nchunks = (n + 31) / 32;
-    int64_t *amb = nullptr;
-    unsigned int *amb_count = nullptr;
-    int rc = TECGAT_OK;
     auto fail = [&](int code) {
-        cudaFree(amb);
-        cudaFree(amb_count);
         tecgraph_ctx_destroy(c);
         return code;
     };
@@ -216,41 +312,55 @@ extern "C" int tecgraph_edges_count(const double *lat, const double *lon, int64_
             return fail(TECGAT_ECUDA);                                                                \
         }                                                                                             \
     } while (0)
-    TG_TRY(cudaMalloc(&c->lat, sizeof(double) * n));
-    TG_TRY(cudaMalloc(&c->lon, sizeof(double) * n));
-    TG_TRY(cudaMalloc(&c->cmin, sizeof(double) * nchunks));
-    TG_TRY(cudaMalloc(&c->cmax, sizeof(double) * nchunks));
-    TG_TRY(cudaMalloc(&c->deg, sizeof(int32_t) * n));
-    TG_TRY(cudaMalloc(&c->rowptr, sizeof(int64_t) * (n + 1)));
-    TG_TRY(cudaMalloc(&amb, sizeof(int64_t) * kMaxAmbiguous));
-    TG_TRY(cudaMalloc(&amb_count, sizeof(unsigned int)));
+    {   // one allocation for every device array of the build (the per-call cudaMalloc x8 used to dominate small graphs)
+        size_t off = 0;
+        auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~size_t(255); return o; };
+        const size_t o_lat = take(8 * n), o_lon = take(8 * n), o_clat = take(8 * n), o_cmin = take(8 * nchunks), o_cmax = take(8 * nchunks),
+                     o_lmin = take(8 * nchunks), o_lmax = take(8 * nchunks), o_ccos = take(8 * nchunks), o_deg = take(4 * n),
+                     o_ev = take(4 * n), o_rp = take(8 * (n + 1)), o_tot = take(64), o_amb = take(8 * size_t(kMaxAmbiguous));
+        TG_TRY(cudaMalloc(reinterpret_cast<void **>(&c->slab), off));
+        unsigned char *b = c->slab;
+        c->lat = reinterpret_cast<double *>(b + o_lat); c->lon = reinterpret_cast<double *>(b + o_lon); c->clat = reinterpret_cast<double *>(b + o_clat);
+        c->cmin = reinterpret_cast<double *>(b + o_cmin); c->cmax = reinterpret_cast<double *>(b + o_cmax);
+        c->lmin = reinterpret_cast<double *>(b + o_lmin); c->lmax = reinterpret_cast<double *>(b + o_lmax); c->ccos = reinterpret_cast<double *>(b + o_ccos);
+        c->deg = reinterpret_cast<int32_t *>(b + o_deg); c->evals = reinterpret_cast<int32_t *>(b + o_ev);
+        c->rowptr = reinterpret_cast<int64_t *>(b + o_rp); c->totals = reinterpret_cast<int64_t *>(b + o_tot); c->amb = reinterpret_cast<int64_t *>(b + o_amb);
+    }
+    for (cudaEvent_t &e : c->ev) TG_TRY(cudaEventCreate(&e));
     TG_TRY(cudaMemcpyAsync(c->lat, lat, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
     TG_TRY(cudaMemcpyAsync(c->lon, lon, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
-    TG_TRY(cudaMemsetAsync(amb_count, 0, sizeof(unsigned int), st));
-    chunk_range_kernel<<<(unsigned)((nchunks + 255) / 256), 256, 0, st>>>(c->lat, n, c->cmin, c->cmax); tg_count_launch();
+    TG_TRY(cudaMemsetAsync(c->totals, 0, 64, st));
+    node_cos_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->lat, n, c->clat); tg_count_launch();
+    chunk_range_kernel<<<(unsigned)((nchunks + 255) / 256), 256, 0, st>>>(c->lat, c->lon, c->clat, n, c->cmin, c->cmax, c->lmin, c->lmax, c->ccos);
+    tg_count_launch();
     TG_TRY(cudaGetLastError());
     const unsigned blocks = (unsigned)((n * 32 + 255) / 256);
-    edges_kernel<false><<<blocks, 256, 0, st>>>(c->lat, c->lon, n, thr_km, radius_km, c->cmin, c->cmax, c->deg, amb, amb_count,
-                                                 nullptr, 0, nullptr, nullptr, nullptr, 0); tg_count_launch();
+    TG_TRY(cudaEventRecord(c->ev[0], st));
+    edges_kernel<false><<<blocks, 256, 0, st>>>(edge_args(c)); tg_count_launch();
+    TG_TRY(cudaEventRecord(c->ev[1], st));
     TG_TRY(cudaGetLastError());
-    std::vector<int32_t> deg(n);
-    unsigned int namb = 0;
-    TG_TRY(cudaMemcpyAsync(deg.data(), c->deg, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
-    TG_TRY(cudaMemcpyAsync(&namb, amb_count, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    scan_kernel<<<1, 1024, 0, st>>>(c->deg, c->evals, n, c->rowptr, c->totals); tg_count_launch();
+    int64_t totals[3] = {0, 0, 0};
+    TG_TRY(cudaMemcpyAsync(totals, c->totals, sizeof(totals), cudaMemcpyDeviceToHost, st));
     TG_TRY(cudaStreamSynchronize(st));
+    const unsigned int namb = static_cast<unsigned int>(totals[2] & 0xFFFFFFFFll);
+    c->total = totals[0];
+    c->evaluated = totals[1];
+    c->ambiguous = namb;
     if (namb > (unsigned)kMaxAmbiguous) {
         tecgat_set_error("edges_count: %u pairs fall in the guard band (capacity %d)", namb, kMaxAmbiguous);
         return fail(TECGAT_ENOSUP);
     }
     if (ambiguous_host) *ambiguous_host = namb;
     // ---- guard band: the host libm decides, in the reference's operation order ----------------------------------
-    std::vector<int64_t> extra;
     if (namb > 0) {
-        std::vector<int64_t> keys(namb);
+        std::vector<int64_t> keys(namb), extra;
         std::vector<double> hlat(n), hlon(n);
-        TG_TRY(cudaMemcpyAsync(keys.data(), amb, sizeof(int64_t) * namb, cudaMemcpyDeviceToHost, st));
+        std::vector<int32_t> deg(n);
+        TG_TRY(cudaMemcpyAsync(keys.data(), c->amb, sizeof(int64_t) * namb, cudaMemcpyDeviceToHost, st));
         TG_TRY(cudaMemcpyAsync(hlat.data(), c->lat, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
         TG_TRY(cudaMemcpyAsync(hlon.data(), c->lon, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+        TG_TRY(cudaMemcpyAsync(deg.data(), c->deg, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
         TG_TRY(cudaStreamSynchronize(st));
         std::sort(keys.begin(), keys.end());
         for (int64_t key : keys) {
@@ -264,19 +374,14 @@ extern "C" int tecgraph_edges_count(const double *lat, const double *lon, int64_
             TG_TRY(cudaMalloc(&c->extra, sizeof(int64_t) * extra.size()));
             TG_TRY(cudaMemcpyAsync(c->extra, extra.data(), sizeof(int64_t) * extra.size(), cudaMemcpyHostToDevice, st));
             TG_TRY(cudaMemcpyAsync(c->deg, deg.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+            scan_kernel<<<1, 1024, 0, st>>>(c->deg, nullptr, n, c->rowptr, c->totals); tg_count_launch();
+            TG_TRY(cudaMemcpyAsync(totals, c->totals, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+            TG_TRY(cudaStreamSynchronize(st));
+            c->total = totals[0];
         }
         c->num_extra = (int64_t)extra.size();
     }
-    std::vector<int64_t> rowptr(n + 1);
-    rowptr[0] = 0;
-    for (int64_t i = 0; i < n; ++i) rowptr[i + 1] = rowptr[i] + deg[i];
-    c->total = rowptr[n];
-    TG_TRY(cudaMemcpyAsync(c->rowptr, rowptr.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, st));
-    TG_TRY(cudaStreamSynchronize(st));
 #undef TG_TRY
-    cudaFree(amb);
-    cudaFree(amb_count);
-    (void)rc;
     *total_host = c->total;
     *ctx_out = c;
     return TECGAT_OK;
@@ -289,8 +394,32 @@ extern "C" int tecgraph_edges_fill(tecgraph_ctx_t *c, int64_t *edge_index, float
     TG_REQUIRE(edge_index && edge_weight, TECGAT_EINVAL, "edges_fill: NULL output");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const unsigned blocks = (unsigned)((c->n * 32 + 255) / 256);
-    edges_kernel<true><<<blocks, 256, 0, st>>>(c->lat, c->lon, c->n, c->thr, c->radius, c->cmin, c->cmax, c->deg, nullptr, nullptr,
-                                                c->extra, c->num_extra, c->rowptr, edge_index, edge_weight, c->total); tg_count_launch();
+    EdgeArgs a = edge_args(c);
+    a.edge_index = edge_index;
+    a.edge_weight = edge_weight;
+    TG_CUDA(cudaEventRecord(c->ev[2], st));
+    edges_kernel<true><<<blocks, 256, 0, st>>>(a); tg_count_launch();
+    TG_CUDA(cudaEventRecord(c->ev[3], st));
+    c->filled = true;
     TG_LAUNCH_CHECK();
+    return TECGAT_OK;
+}
+
+// stats4 = {count-kernel ms, fill-kernel ms (0 before tecgraph_edges_fill), pairs evaluated by the count pass, guard-band pairs};
+// synchronises the fill kernel's event
+extern "C" int tecgraph_ctx_stats(tecgraph_ctx_t *c, double *stats4_host) {
+    TG_REQUIRE(c && stats4_host, TECGAT_EINVAL, "ctx_stats: NULL argument");
+    float ms = 0.f;
+    TG_CUDA(cudaEventSynchronize(c->ev[1]));
+    TG_CUDA(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
+    stats4_host[0] = ms;
+    stats4_host[1] = 0.0;
+    if (c->filled) {
+        TG_CUDA(cudaEventSynchronize(c->ev[3]));
+        TG_CUDA(cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]));
+        stats4_host[1] = ms;
+    }
+    stats4_host[2] = (double)c->evaluated;
+    stats4_host[3] = (double)c->ambiguous;
     return TECGAT_OK;
 }

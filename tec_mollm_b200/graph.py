@@ -65,10 +65,14 @@ def build_graph_from_nodes(lat_rad, lon_rad, distance_threshold_km: float = 150.
             edge_weight = torch.empty((total.value,), dtype=torch.float32, device=dev)
             _lib.call("tecgraph_edges_fill", ctx, _ptr(edge_index), _ptr(edge_weight), _stream(dev))
             torch.cuda.current_stream(dev).synchronize()  # the context owns device buffers the kernel reads
+            st4 = (C.c_double * 4)()
+            if return_stats:
+                _lib.call("tecgraph_ctx_stats", ctx, st4)
         finally:
             _lib.lib().tecgraph_ctx_destroy(ctx)
     if return_stats:
-        return edge_index, edge_weight, {"guard_band_pairs": int(amb.value), "num_nodes": n}
+        return edge_index, edge_weight, {"guard_band_pairs": int(amb.value), "num_nodes": n, "count_kernel_ms": st4[0],
+                                         "fill_kernel_ms": st4[1], "kernel_ms": st4[0] + st4[1], "evaluated_pairs": int(st4[2])}
     return edge_index, edge_weight
 
 
