@@ -132,7 +132,7 @@ extern "C" int tecgat_backward(const tecgat_plan_t *plan, const float *x, const 
     const int64_t rows = int64_t(snapshots) * plan->num_nodes;
     unsigned char *ws1 = static_cast<unsigned char *>(workspace);
     unsigned char *ws2 = ws1 + align256(tecgat_edge_bwd_workspace(plan, snapshots, heads, out_channels));
-    const bool fused = impl == TECGAT_PROJ_TC && tg_env("TECGAT_PROJ_BWD") == nullptr && project_bwd_rt_supported(F, HC, dxl, dxr, x, dx);
+    const bool fused = impl == TECGAT_PROJ_TC && project_bwd_rt_supported(F, HC, dxl, dxr, x, dx);  // (implies the tc kernel's range too)
     TG_REQUIRE(fused || (!grad_accumulate && !dx_accumulate), TECGAT_ENOSUP,
                "backward: in-place accumulation needs the register-tiled projection backward (F=%d, H*C=%d, 16-byte aligned "
                "buffers); call without accumulation", F, HC);
@@ -149,7 +149,10 @@ extern "C" int tecgat_backward(const tecgat_plan_t *plan, const float *x, const 
     }
     ReduceJob jobs[2];
     jobs[0] = ReduceJob{reinterpret_cast<const float *>(ws1), edge_rows, 2 * HC, {{datt, dbias, nullptr, nullptr}, {0, HC, 0, 0}, {HC, 2 * HC, 0, 0}}};
-    rc = project_bwd_rt(dxl, dxr, x, wl, wr, dx, dwl, dbl, dwr, dbr, ws2, rows, F, HC, dtype, st, dx_accumulate != 0, &jobs[1]);
+    if (project_bwd_use_tc(F, HC, dtype, dxl, dxr, x, dx))
+        rc = project_bwd_tc(dxl, dxr, x, wl, wr, dx, dwl, dbl, dwr, dbr, ws2, rows, F, HC, dtype, st, dx_accumulate != 0, &jobs[1]);
+    else
+        rc = project_bwd_rt(dxl, dxr, x, wl, wr, dx, dwl, dbl, dwr, dbr, ws2, rows, F, HC, dtype, st, dx_accumulate != 0, &jobs[1]);
     if (rc != TECGAT_OK) return rc;
     rc = reduce_columns_multi(jobs, 2, grad_accumulate, st);
     phase_mark(3, st);

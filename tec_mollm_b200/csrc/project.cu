@@ -18,6 +18,16 @@ extern "C" int tecgat_project_fwd(const float *x, const float *wl, const float *
     return tg::project_fwd_tc(x, wl, bl, wr, br, xl, xr, rows, F, hc, dtype, st);
 }
 
+bool tg::project_bwd_use_tc(int F, int HC, int dtype, const void *dxl, const void *dxr, const void *x, const void *dx) {
+    const char *env = tg_env("TECGAT_PROJ_BWD");
+    const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dxl) | reinterpret_cast<uintptr_t>(dxr) |
+                           reinterpret_cast<uintptr_t>(dx)) & 15) == 0;
+    if (!aligned || !tg::project_bwd_tc_supported(F, HC, dtype)) return false;
+    if (env && env[0] == 't') return true;
+    if (env && env[0] == 'r') return false;
+    return dtype == TECGAT_BF16 || !tg::project_bwd_rt_supported(F, HC, dxl, dxr, x, dx);
+}
+
 extern "C" int64_t tecgat_project_bwd_workspace(int64_t rows, int32_t F, int32_t hc, int32_t impl) {
     if (rows <= 0 || F <= 0 || hc <= 0) return 0;
     if (impl == TECGAT_PROJ_FFMA) return tg::project_bwd_ffma_workspace(rows, F, hc);
@@ -35,11 +45,8 @@ extern "C" int tecgat_project_bwd(const void *dxl, const void *dxr, const float 
     if (impl == TECGAT_PROJ_FFMA)
         return tg::project_bwd_ffma(dxl, dxr, x, wl, wr, dx, dwl, dbl, dwr, dbr, workspace, rows, F, hc, dtype, st);
     TG_REQUIRE(impl == TECGAT_PROJ_TC, TECGAT_EINVAL, "project_bwd: bad impl %d", impl);
-    // Product path: the register-tiled packed-fp32 kernel (project_bwd_rt.cu explains why the backward is not on tcgen05);
-    // TECGAT_PROJ_BWD=tc selects the tcgen05 kernel (kept for the bf16 contract experiments and as a cross-check).
-    const char *env = getenv("TECGAT_PROJ_BWD");
-    const bool force_tc = env && env[0] == 't';
-    if (!force_tc && tg::project_bwd_rt_supported(F, hc, dxl, dxr, x, dx))
+    // Product path (project.cuh): tcgen05 for the bf16 contract, the register-tiled packed-fp32 kernel for the fp32 contract.
+    if (!tg::project_bwd_use_tc(F, hc, dtype, dxl, dxr, x, dx) && tg::project_bwd_rt_supported(F, hc, dxl, dxr, x, dx))
         return tg::project_bwd_rt(dxl, dxr, x, wl, wr, dx, dwl, dbl, dwr, dbr, workspace, rows, F, hc, dtype, st);
     return tg::project_bwd_tc(dxl, dxr, x, wl, wr, dx, dwl, dbl, dwr, dbr, workspace, rows, F, hc, dtype, st);
 }
@@ -47,8 +54,6 @@ extern "C" int tecgat_project_bwd(const void *dxl, const void *dxr, const float 
 // dx += dxl Wl + dxr Wr: the caller pre-loaded dx (the spatial block's residual-branch gradient, permute.cu), so autograd's
 // separate accumulation pass disappears.  Only the register-tiled kernel implements it (a bulk-TMA reduction store).
 extern "C" int tecgat_project_bwd_acc_supported(int32_t F, int32_t hc) {
-    const char *env = getenv("TECGAT_PROJ_BWD");
-    if (env && env[0] == 't') return 0;
     return tg::project_bwd_rt_supported(F, hc, nullptr, nullptr, nullptr, nullptr) ? 1 : 0;
 }
 
@@ -61,6 +66,8 @@ extern "C" int tecgat_project_bwd_acc(const void *dxl, const void *dxr, const fl
     TG_REQUIRE(tg::project_bwd_rt_supported(F, hc, dxl, dxr, x, dx), TECGAT_ENOSUP,
                "project_bwd_acc: F=%d, H*C=%d (or a pointer that is not 16-byte aligned) is outside the accumulating kernel's range; "
                "call tecgat_project_bwd and add", F, hc);
+    if (tg::project_bwd_use_tc(F, hc, dtype, dxl, dxr, x, dx))
+        return tg::project_bwd_tc(dxl, dxr, x, wl, wr, dx, dwl, dbl, dwr, dbr, workspace, rows, F, hc, dtype, static_cast<cudaStream_t>(stream), true);
     return tg::project_bwd_rt(dxl, dxr, x, wl, wr, dx, dwl, dbl, dwr, dbr, workspace, rows, F, hc, dtype,
                               static_cast<cudaStream_t>(stream), true);
 }

@@ -411,6 +411,7 @@ struct TcBwdArgs {
     const void *dxl, *dxr;
     const float *x, *wl, *wr;
     float *dx;        // may be NULL (input does not require grad): GEMM1 is skipped
+    int32_t accumulate;  // dx += (the caller pre-loaded dx with the residual branch's gradient) instead of dx =
     float *partials;  // (grid, 2*HC*F + 2*HC): [dWl | dWr | dbl | dbr] per CTA
     int64_t R;
     int32_t F, HC;
@@ -482,8 +483,10 @@ __device__ __forceinline__ void write_row_bf16(unsigned char *base, uint32_t spl
 // the products kept by the split GEMM, smallest first: (a-term, b-term)
 __device__ __constant__ int kSplitPairs[6][2] = {{0, 2}, {2, 0}, {1, 1}, {0, 1}, {1, 0}, {0, 0}};
 
+// bf16 contract (SPLIT = 1): ~103 KB of shared memory and 128 TMEM columns per CTA -> TWO CTAs per SM, so one CTA's
+// TMA -> re-layout -> MMA -> epilogue latency chain overlaps the other's
 template <int SPLIT>
-__global__ void __launch_bounds__(kBwdThreads, 1) project_bwd_tc_kernel(const TcBwdArgs a) {
+__global__ void __launch_bounds__(kBwdThreads, SPLIT == 1 ? 2 : 1) project_bwd_tc_kernel(const TcBwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     using ST = typename std::conditional<SPLIT == 1, __nv_bfloat16, float>::type;
     const int F = a.F, HC = a.HC, O = 2 * a.HC, OP = a.OP, N1 = a.N1, NP2 = a.NP2, nst = a.stages;
@@ -615,7 +618,38 @@ __global__ void __launch_bounds__(kBwdThreads, 1) project_bwd_tc_kernel(const Tc
                 if (it >= 1) mbar_wait(ops_free, (it - 1) & 1);
                 const unsigned char *st = smem + L.stage0 + s * L.stage_bytes;
                 const bool live = row < nr;  // rows past the end of the last tile must contribute ZERO to GEMM2
-                if (half == 0) {
+                if (SPLIT == 1 && F == 22 && HC == 22) {
+                    // the reference's shape, bf16 contract: the gradient rows already are bf16 (11 words each), so the re-layout
+                    // is a copy into the 16-byte chunks of the canonical layout; x is converted pairwise.  Straight-line.
+                    if (half == 0) {
+                        const uint32_t *gl = reinterpret_cast<const uint32_t *>(st + (size_t)row * 44);
+                        const uint32_t *gr = reinterpret_cast<const uint32_t *>(st + L.tile_d + (size_t)row * 44);
+                        uint32_t w[24];
+#pragma unroll
+                        for (int i = 0; i < 11; ++i) {
+                            w[i] = live ? gl[i] : 0u;
+                            w[11 + i] = live ? gr[i] : 0u;
+                        }
+                        w[22] = w[23] = 0u;
+#pragma unroll
+                        for (int kc = 0; kc < 6; ++kc)
+                            *reinterpret_cast<uint4 *>(smem + L.d + canon_off(row, kc, L.P_d)) = make_uint4(w[4 * kc], w[4 * kc + 1], w[4 * kc + 2], w[4 * kc + 3]);
+                    } else {
+                        const float2 *xrow = reinterpret_cast<const float2 *>(st + 2 * L.tile_d + (size_t)row * 88);
+                        uint32_t w[16];
+#pragma unroll
+                        for (int i = 0; i < 11; ++i) {
+                            const float2 v = xrow[i];
+                            const __nv_bfloat162 h = __floats2bfloat162_rn(v.x, v.y);
+                            w[i] = live ? *reinterpret_cast<const uint32_t *>(&h) : 0u;
+                        }
+                        w[11] = live ? 0x00003F80u : 0u;  // bf16(1.0) in column F: the bias gradients fall out of GEMM2
+                        w[12] = w[13] = w[14] = w[15] = 0u;
+#pragma unroll
+                        for (int kc = 0; kc < 4; ++kc)
+                            *reinterpret_cast<uint4 *>(smem + L.x + canon_off(row, kc, L.P_x)) = make_uint4(w[4 * kc], w[4 * kc + 1], w[4 * kc + 2], w[4 * kc + 3]);
+                    }
+                } else if (half == 0) {
                     const ST *gl = reinterpret_cast<const ST *>(st) + row * HC;
                     const ST *gr = reinterpret_cast<const ST *>(st + L.tile_d) + row * HC;
                     write_row_bf16<SPLIT>(smem + L.d, L.d_bytes, row, L.P_d, live ? O : 0, OP,
@@ -655,9 +689,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) project_bwd_tc_kernel(const Tc
                 float *gdx = a.dx + r0 * F;
                 if (nr == kTileM) {
                     if (issuer) {
-                        bulk_s2g(gdx, dx_st, kTileM * F * 4u);
+                        if (a.accumulate) bulk_s2g_add_f32(gdx, dx_st, kTileM * F * 4u);  // one add per element: deterministic
+                        else bulk_s2g(gdx, dx_st, kTileM * F * 4u);
                         bulk_commit();
                     }
+                } else if (a.accumulate) {
+                    for (int i = wt; i < nr * F; i += kBwdWorkers) gdx[i] += dx_st[i];
                 } else {
                     for (int i = wt; i < nr * F; i += kBwdWorkers) gdx[i] = dx_st[i];
                 }
@@ -702,8 +739,9 @@ static bool bwd_tc_config(TcBwdArgs &a) {
     a.d2_col = 2 * a.d1_stride;
     a.tmem_cols = pow2_cols(a.d2_col + a.NP2);
     if (a.tmem_cols > 512) return false;
+    const uint32_t budget = SPLIT == 1 ? 110u * 1024u : 220u * 1024u;  // two CTAs per SM for the bf16 contract
     for (a.stages = kBwdMaxStages; a.stages >= 1; --a.stages)
-        if (tc_bwd_smem<SPLIT>(a.F, a.HC, a.OP, a.N1, a.NP2, a.stages).total <= 220u * 1024u) return true;
+        if (tc_bwd_smem<SPLIT>(a.F, a.HC, a.OP, a.N1, a.NP2, a.stages).total <= budget) return true;
     return false;
 }
 
@@ -713,9 +751,9 @@ bool project_bwd_tc_supported(int F, int HC, int dtype) {
     return dtype == TECGAT_BF16 ? bwd_tc_config<1>(a) : bwd_tc_config<3>(a);
 }
 
-static int bwd_tc_grid(int64_t R) {
-    const int64_t tiles = (R + kTileM - 1) / kTileM;
-    return (int)(tiles < 148 ? tiles : 148);
+static int bwd_tc_grid(int64_t R, int ctas_per_sm = 2) {
+    const int64_t tiles = (R + kTileM - 1) / kTileM, cap = int64_t(ctas_per_sm) * tg_sm_count();
+    return (int)(tiles < cap ? tiles : cap);
 }
 
 int64_t project_bwd_tc_workspace(int64_t R, int F, int HC) {
@@ -725,30 +763,37 @@ int64_t project_bwd_tc_workspace(int64_t R, int F, int HC) {
 }
 
 template <int SPLIT>
-static int launch_bwd_tc(TcBwdArgs &a, float *dwl, float *dbl, float *dwr, float *dbr, cudaStream_t st) {
+static int launch_bwd_tc(TcBwdArgs &a, float *dwl, float *dbl, float *dwr, float *dbr, cudaStream_t st, ReduceJob *defer) {
     bwd_tc_config<SPLIT>(a);
     const TcBwdSmem L = tc_bwd_smem<SPLIT>(a.F, a.HC, a.OP, a.N1, a.NP2, a.stages);
     auto kern = project_bwd_tc_kernel<SPLIT>;
     TG_CUDA(tg_set_smem(reinterpret_cast<const void *>(kern), (int)L.total));
-    const int grid = bwd_tc_grid(a.R);
+    const int grid = bwd_tc_grid(a.R, SPLIT == 1 ? 2 : 1);
     kern<<<grid, kBwdThreads, L.total, st>>>(a); tg_count_launch();
     TG_LAUNCH_CHECK();
     const int O = 2 * a.HC, F = a.F, HC = a.HC;
     ReduceSegs segs = {{dwl, dwr, dbl, dbr}, {0, HC * F, O * F, O * F + HC}, {HC * F, O * F, O * F + HC, O * F + O}};
+    if (defer) {  // the caller finishes these partials together with the edge kernel's in one launch
+        *defer = ReduceJob{a.partials, grid, O * F + O, segs};
+        return TECGAT_OK;
+    }
     return reduce_columns(a.partials, grid, O * F + O, segs, st);
 }
 
 int project_bwd_tc(const void *dxl, const void *dxr, const float *x, const float *wl, const float *wr, float *dx,
                    float *dwl, float *dbl, float *dwr, float *dbr, void *workspace, int64_t R, int F, int HC, int dtype,
-                   cudaStream_t st) {
+                   cudaStream_t st, bool accumulate, ReduceJob *defer) {
     const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dxl) | reinterpret_cast<uintptr_t>(dxr) |
                            reinterpret_cast<uintptr_t>(dx)) & 15) == 0;
-    if (!aligned || !project_bwd_tc_supported(F, HC, dtype))  // shapes beyond the tensor-core kernel's shared-memory budget
+    if (!aligned || !project_bwd_tc_supported(F, HC, dtype)) {  // shapes beyond the tensor-core kernel's shared-memory budget
+        TG_REQUIRE(!accumulate && !defer, TECGAT_ENOSUP, "project_bwd(tc): F=%d, H*C=%d unsupported with accumulation", F, HC);
         return project_bwd_ffma(dxl, dxr, x, wl, wr, dx, dwl, dbl, dwr, dbr, workspace, R, F, HC, dtype, st);
+    }
     TcBwdArgs a{};
     a.dxl = dxl; a.dxr = dxr; a.x = x; a.wl = wl; a.wr = wr; a.dx = dx; a.partials = static_cast<float *>(workspace);
+    a.accumulate = accumulate ? 1 : 0;
     a.R = R; a.F = F; a.HC = HC;
-    return dtype == TECGAT_BF16 ? launch_bwd_tc<1>(a, dwl, dbl, dwr, dbr, st) : launch_bwd_tc<3>(a, dwl, dbl, dwr, dbr, st);
+    return dtype == TECGAT_BF16 ? launch_bwd_tc<1>(a, dwl, dbl, dwr, dbr, st, defer) : launch_bwd_tc<3>(a, dwl, dbl, dwr, dbr, st, defer);
 }
 
 }  // namespace tg
