@@ -17,6 +17,7 @@
 #include <math.h>
 
 #include <algorithm>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -38,6 +39,7 @@ struct tecgraph_ctx {
     int64_t total = 0, evaluated = 0, ambiguous = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // count kernel begin/end, fill kernel begin/end
     bool filled = false;
+    cudaStream_t stream = nullptr;          // the stream the slab was allocated on (stream-ordered allocation)
 };
 
 namespace tg {
@@ -262,7 +264,7 @@ extern "C" int tecgraph_distance_rows(const double *lat, const double *lon, int6
 
 extern "C" int tecgraph_ctx_destroy(tecgraph_ctx_t *c) {
     if (!c) return TECGAT_OK;
-    cudaFree(c->slab);
+    if (c->slab) cudaFreeAsync(c->slab, c->stream);  // back to the device's memory pool: the next build reuses it
     cudaFree(c->extra);
     for (cudaEvent_t e : c->ev)
         if (e) cudaEventDestroy(e);
@@ -318,7 +320,22 @@ extern "C" int tecgraph_edges_count(const double *lat, const double *lon, int64_
         const size_t o_lat = take(8 * n), o_lon = take(8 * n), o_clat = take(8 * n), o_cmin = take(8 * nchunks), o_cmax = take(8 * nchunks),
                      o_lmin = take(8 * nchunks), o_lmax = take(8 * nchunks), o_ccos = take(8 * nchunks), o_deg = take(4 * n),
                      o_ev = take(4 * n), o_rp = take(8 * (n + 1)), o_tot = take(64), o_amb = take(8 * size_t(kMaxAmbiguous));
-        TG_TRY(cudaMalloc(reinterpret_cast<void **>(&c->slab), off));
+        {   // stream-ordered allocation from the device's default pool, kept warm: a build is a few hundred microseconds of
+            // kernels, and cudaMalloc / cudaFree (device-wide synchronisation, page mapping) used to cost 10x that
+            static std::once_flag pool_once[64];
+            int dev = 0;
+            TG_TRY(cudaGetDevice(&dev));
+            if (dev >= 0 && dev < 64)
+                std::call_once(pool_once[dev], [dev] {
+                    cudaMemPool_t pool;
+                    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                        uint64_t keep = UINT64_MAX;
+                        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+                    }
+                });
+        }
+        c->stream = st;
+        TG_TRY(cudaMallocAsync(reinterpret_cast<void **>(&c->slab), off, st));
         unsigned char *b = c->slab;
         c->lat = reinterpret_cast<double *>(b + o_lat); c->lon = reinterpret_cast<double *>(b + o_lon); c->clat = reinterpret_cast<double *>(b + o_clat);
         c->cmin = reinterpret_cast<double *>(b + o_cmin); c->cmax = reinterpret_cast<double *>(b + o_cmax);

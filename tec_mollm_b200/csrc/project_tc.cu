@@ -443,7 +443,7 @@ __host__ __device__ inline TcBwdSmem tc_bwd_smem(int F, int HC, int OP, int N1, 
     s.tile_x = ((kTileM * F * 4 + 127) / 128) * 128;
     s.stage_bytes = 2 * s.tile_d + s.tile_x;
     s.stage0 = o; o += stages * s.stage_bytes;
-    s.dx_st = o; o += s.tile_x;
+    s.dx_st = o; o += SPLIT == 1 ? s.tile_x : 0;  // fp32 contract: dx is stored straight from registers
     s.total = o;
     return s;
 }
@@ -483,10 +483,14 @@ __device__ __forceinline__ void write_row_bf16(unsigned char *base, uint32_t spl
 // the products kept by the split GEMM, smallest first: (a-term, b-term)
 __device__ __constant__ int kSplitPairs[6][2] = {{0, 2}, {2, 0}, {1, 1}, {0, 1}, {1, 0}, {0, 0}};
 
-// bf16 contract (SPLIT = 1): ~103 KB of shared memory and 128 TMEM columns per CTA -> TWO CTAs per SM, so one CTA's
-// TMA -> re-layout -> MMA -> epilogue latency chain overlaps the other's
+// <= 110 KB of shared memory and 128 TMEM columns per CTA -> TWO CTAs per SM, so one CTA's TMA -> re-layout -> MMA -> epilogue
+// latency chain overlaps the other's (bf16 contract: three ring stages; fp32 contract: the three split terms of both operand
+// buffers leave room for one stage, and dx leaves straight from registers instead of through a staging tile).
+// fp32 contract: GEMM2's TMEM accumulator is flushed into per-thread fp64 sums every kD2FlushTiles tiles (4,096 rows), so the
+// weight gradients do not accumulate fp32 rounding over the CTA's whole share of the rows (~60 k).
+constexpr int kD2FlushTiles = 32;
 template <int SPLIT>
-__global__ void __launch_bounds__(kBwdThreads, SPLIT == 1 ? 2 : 1) project_bwd_tc_kernel(const TcBwdArgs a) {
+__global__ void __launch_bounds__(kBwdThreads, 2) project_bwd_tc_kernel(const TcBwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     using ST = typename std::conditional<SPLIT == 1, __nv_bfloat16, float>::type;
     const int F = a.F, HC = a.HC, O = 2 * a.HC, OP = a.OP, N1 = a.N1, NP2 = a.NP2, nst = a.stages;
@@ -587,6 +591,7 @@ __global__ void __launch_bounds__(kBwdThreads, SPLIT == 1 ? 2 : 1) project_bwd_t
                     }
                     umma_commit(&t_full[it & 1]);
                 }
+                if (SPLIT == 3 && NP2 <= 32 && (it % kD2FlushTiles) == 0) acc2 = 0;  // the workers flushed D2 into their fp64 sums
                 for (int ks = 0; ks < ksteps2; ++ks) {
                     const uint32_t da = ks * 2 * L.P_d, dbx = ks * 2 * L.P_x;
                     for (int q = 0; q < nprod; ++q) {
@@ -608,6 +613,11 @@ __global__ void __launch_bounds__(kBwdThreads, SPLIT == 1 ? 2 : 1) project_bwd_t
         const int wt = (warp - 2) * 32 + lane;  // 0..255
         const bool issuer = (wt == 0);
         float *dx_st = reinterpret_cast<float *>(smem + L.dx_st);
+        const bool d2_flush = SPLIT == 3 && NP2 <= 32;  // one 16-column block of D2 per thread
+        double acc2d[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc2d[i] = 0.0;
+        const uint32_t taddr2 = tmem_base + ((uint32_t)(quarter * 32) << 16) + a.d2_col;
         for (int it = 0; it <= n_local; ++it) {
             if (it < n_local) {
                 const int s = it % nst;
@@ -616,6 +626,16 @@ __global__ void __launch_bounds__(kBwdThreads, SPLIT == 1 ? 2 : 1) project_bwd_t
                 const int nr = (int)((a.R - r0) < (int64_t)kTileM ? (a.R - r0) : (int64_t)kTileM);
                 mbar_wait(&full[s], (it / nst) & 1);
                 if (it >= 1) mbar_wait(ops_free, (it - 1) & 1);
+                if (d2_flush && it >= 1 && (it % kD2FlushTiles) == 0) {
+                    // every MMA up to tile it-1 has completed and none of tile it can start before all workers arrive below:
+                    // D2 is quiescent.  Move it into the fp64 sums; the issuer restarts the accumulator with this tile.
+                    tc_fence_after();
+                    float v[16];
+                    tmem_ld16(taddr2 + half * 16, v);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) acc2d[i] += (double)v[i];
+                    tc_fence_before();
+                }
                 const unsigned char *st = smem + L.stage0 + s * L.stage_bytes;
                 const bool live = row < nr;  // rows past the end of the last tile must contribute ZERO to GEMM2
                 if (SPLIT == 1 && F == 22 && HC == 22) {
@@ -649,6 +669,56 @@ __global__ void __launch_bounds__(kBwdThreads, SPLIT == 1 ? 2 : 1) project_bwd_t
                         for (int kc = 0; kc < 4; ++kc)
                             *reinterpret_cast<uint4 *>(smem + L.x + canon_off(row, kc, L.P_x)) = make_uint4(w[4 * kc], w[4 * kc + 1], w[4 * kc + 2], w[4 * kc + 3]);
                     }
+                } else if (SPLIT == 3 && F == 22 && HC == 22) {
+                    // the reference's shape, fp32 contract: v = b0 + b1 + b2 in three bf16 terms, straight-line
+                    auto split3 = [&](float v0, float v1, uint32_t &o0, uint32_t &o1, uint32_t &o2) {
+                        const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+                        const float2 hf = __bfloat1622float2(h);
+                        const float r0 = v0 - hf.x, r1 = v1 - hf.y;  // exact
+                        const __nv_bfloat162 m = __floats2bfloat162_rn(r0, r1);
+                        const float2 mf = __bfloat1622float2(m);
+                        const __nv_bfloat162 l = __floats2bfloat162_rn(r0 - mf.x, r1 - mf.y);
+                        o0 = *reinterpret_cast<const uint32_t *>(&h);
+                        o1 = *reinterpret_cast<const uint32_t *>(&m);
+                        o2 = *reinterpret_cast<const uint32_t *>(&l);
+                    };
+                    if (half == 0) {
+                        const float2 *gl = reinterpret_cast<const float2 *>(st + (size_t)row * 88);
+                        const float2 *gr = reinterpret_cast<const float2 *>(st + L.tile_d + (size_t)row * 88);
+                        uint32_t w0[24], w1[24], w2[24];
+#pragma unroll
+                        for (int i = 0; i < 22; ++i) {
+                            const float2 v = i < 11 ? gl[i] : gr[i - 11];
+                            split3(live ? v.x : 0.f, live ? v.y : 0.f, w0[i], w1[i], w2[i]);
+                        }
+                        w0[22] = w0[23] = w1[22] = w1[23] = w2[22] = w2[23] = 0u;
+#pragma unroll
+                        for (int kc = 0; kc < 6; ++kc) {
+                            const uint32_t off = canon_off(row, kc, L.P_d);
+                            *reinterpret_cast<uint4 *>(smem + L.d + off) = make_uint4(w0[4 * kc], w0[4 * kc + 1], w0[4 * kc + 2], w0[4 * kc + 3]);
+                            *reinterpret_cast<uint4 *>(smem + L.d + L.d_bytes + off) = make_uint4(w1[4 * kc], w1[4 * kc + 1], w1[4 * kc + 2], w1[4 * kc + 3]);
+                            *reinterpret_cast<uint4 *>(smem + L.d + 2 * L.d_bytes + off) = make_uint4(w2[4 * kc], w2[4 * kc + 1], w2[4 * kc + 2], w2[4 * kc + 3]);
+                        }
+                    } else {
+                        const float2 *xrow = reinterpret_cast<const float2 *>(st + 2 * L.tile_d + (size_t)row * 88);
+                        uint32_t w0[16], w1[16], w2[16];
+#pragma unroll
+                        for (int i = 0; i < 11; ++i) {
+                            const float2 v = xrow[i];
+                            split3(live ? v.x : 0.f, live ? v.y : 0.f, w0[i], w1[i], w2[i]);
+                        }
+                        w0[11] = live ? 0x00003F80u : 0u;  // the constant-one column: exact in the first term
+                        w1[11] = w2[11] = 0u;
+#pragma unroll
+                        for (int i = 12; i < 16; ++i) w0[i] = w1[i] = w2[i] = 0u;
+#pragma unroll
+                        for (int kc = 0; kc < 4; ++kc) {
+                            const uint32_t off = canon_off(row, kc, L.P_x);
+                            *reinterpret_cast<uint4 *>(smem + L.x + off) = make_uint4(w0[4 * kc], w0[4 * kc + 1], w0[4 * kc + 2], w0[4 * kc + 3]);
+                            *reinterpret_cast<uint4 *>(smem + L.x + L.x_bytes + off) = make_uint4(w1[4 * kc], w1[4 * kc + 1], w1[4 * kc + 2], w1[4 * kc + 3]);
+                            *reinterpret_cast<uint4 *>(smem + L.x + 2 * L.x_bytes + off) = make_uint4(w2[4 * kc], w2[4 * kc + 1], w2[4 * kc + 2], w2[4 * kc + 3]);
+                        }
+                    }
                 } else if (half == 0) {
                     const ST *gl = reinterpret_cast<const ST *>(st) + row * HC;
                     const ST *gr = reinterpret_cast<const ST *>(st + L.tile_d) + row * HC;
@@ -670,9 +740,40 @@ __global__ void __launch_bounds__(kBwdThreads, SPLIT == 1 ? 2 : 1) project_bwd_t
                 const int nr = (int)((a.R - r0) < (int64_t)kTileM ? (a.R - r0) : (int64_t)kTileM);
                 mbar_wait(&t_full[acc], (j >> 1) & 1);
                 tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * a.d1_stride;
+                if (SPLIT == 3) {
+                    // fp32 contract: no staging tile (shared memory is spent on the split operands): each thread owns 16 columns of
+                    // its row and stores them as aligned float2 (rows are F * 4 bytes, F even on this path)
+                    float *grow = a.dx + (r0 + row) * F;
+                    for (int cb = half; cb < N1 / 16; cb += 2) {
+                        float v[16];
+                        tmem_ld16(taddr + cb * 16, v);
+                        if (row < nr) {
+#pragma unroll
+                            for (int i = 0; i < 16; i += 2) {
+                                const int f = cb * 16 + i;
+                                if (f + 1 < F && (F & 1) == 0) {  // even F: every row starts 8-byte aligned
+                                    float2 *dst = reinterpret_cast<float2 *>(grow + f);
+                                    float2 o = make_float2(v[i], v[i + 1]);
+                                    if (a.accumulate) {
+                                        const float2 old = *dst;
+                                        o.x += old.x;
+                                        o.y += old.y;
+                                    }
+                                    *dst = o;
+                                } else {
+                                    if (f < F) grow[f] = a.accumulate ? grow[f] + v[i] : v[i];
+                                    if (f + 1 < F) grow[f + 1] = a.accumulate ? grow[f + 1] + v[i + 1] : v[i + 1];
+                                }
+                            }
+                        }
+                    }
+                    tc_fence_before();
+                    mbar_arrive(&t_empty[acc]);
+                    continue;
+                }
                 if (issuer) bulk_wait_read0();
                 named_bar_sync(1, kBwdWorkers);
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * a.d1_stride;
                 for (int cb = half; cb < N1 / 16; cb += 2) {
                     float v[16];
                     tmem_ld16(taddr + cb * 16, v);
@@ -713,8 +814,9 @@ __global__ void __launch_bounds__(kBwdThreads, SPLIT == 1 ? 2 : 1) project_bwd_t
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         const int n = cb * 16 + i;
-                        if (n < F) out[row * F + n] = v[i];
-                        else if (n == F) out[O * F + row] = v[i];
+                        const float t = d2_flush ? (float)(acc2d[i] + (double)v[i]) : v[i];
+                        if (n < F) out[row * F + n] = t;
+                        else if (n == F) out[O * F + row] = t;
                     }
                 }
             }
@@ -739,7 +841,7 @@ static bool bwd_tc_config(TcBwdArgs &a) {
     a.d2_col = 2 * a.d1_stride;
     a.tmem_cols = pow2_cols(a.d2_col + a.NP2);
     if (a.tmem_cols > 512) return false;
-    const uint32_t budget = SPLIT == 1 ? 110u * 1024u : 220u * 1024u;  // two CTAs per SM for the bf16 contract
+    const uint32_t budget = 110u * 1024u;  // two CTAs per SM
     for (a.stages = kBwdMaxStages; a.stages >= 1; --a.stages)
         if (tc_bwd_smem<SPLIT>(a.F, a.HC, a.OP, a.N1, a.NP2, a.stages).total <= budget) return true;
     return false;
@@ -768,7 +870,7 @@ static int launch_bwd_tc(TcBwdArgs &a, float *dwl, float *dbl, float *dwr, float
     const TcBwdSmem L = tc_bwd_smem<SPLIT>(a.F, a.HC, a.OP, a.N1, a.NP2, a.stages);
     auto kern = project_bwd_tc_kernel<SPLIT>;
     TG_CUDA(tg_set_smem(reinterpret_cast<const void *>(kern), (int)L.total));
-    const int grid = bwd_tc_grid(a.R, SPLIT == 1 ? 2 : 1);
+    const int grid = bwd_tc_grid(a.R, 2);
     kern<<<grid, kBwdThreads, L.total, st>>>(a); tg_count_launch();
     TG_LAUNCH_CHECK();
     const int O = 2 * a.HC, F = a.F, HC = a.HC;
