@@ -312,8 +312,8 @@ __global__ void __launch_bounds__(WG ? 384 : 256, 1) edge_bwd_kernel(const EdgeB
     cv_load_param<C>(attm, a.att + hh * C, par, 0.5f * (1.f - a.slope) * kLog2e);
     cv_load_param<C>(att_h, a.att + hh * C, par, 1.f);
     cv_load_param<C>(bias_h, a.bias + hh * C, par, 1.f);
-    const uint32_t head_key = dropout_head_key((uint32_t)hh);
-    uint32_t key = 0;
+    const DropKeys head_key = dropout_head_keys((uint32_t)hh);
+    uint32_t key = 0, key2 = 0;
     int key_snap = -1;
     const uint64_t seed = (DROP && a.seed_dev) ? __ldg(a.seed_dev) : a.seed;
     // per-lane fp32 partial sums of d att and d bias: one term per item, flushed to a CTA partial row every kFlushItems
@@ -365,12 +365,15 @@ __global__ void __launch_bounds__(WG ? 384 : 256, 1) edge_bwd_kernel(const EdgeB
         const bool active = head_ok && node_l < nt;
         const int64_t row = (int64_t)snap * N + n0 + node_l;
         if (DROP && a.drop_thr && snap != key_snap) {
-            key = dropout_snapshot_key(seed, (uint32_t)snap) ^ head_key;
+            const DropKeys sk = dropout_snapshot_keys(seed, (uint32_t)snap);
+            key = sk.k1 ^ head_key.k1;
+            key2 = sk.k2 ^ head_key.k2;
             key_snap = snap;
         }
         DropCfg<DROP> drop;
         drop.thr = a.drop_thr;
         drop.key = key;
+        drop.key2 = key2;
         drop.inv_keep = a.inv_keep;
         CV<C> dxl, dxr, tatt, g_v;
         if (staged) {

@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) edge_bwd_sw_kernel(const SwArgs
     }
     bar_sync_named(kBarConsumers, nct);
     const float *att_s = prm + h * C, *nbias_s = prm + HC + h * C;
-    const uint32_t head_key = dropout_head_key((uint32_t)h);
+    const DropKeys head_key = dropout_head_keys((uint32_t)h);
     const uint64_t seed = (DROP && a.seed_dev) ? __ldg(a.seed_dev) : a.seed;
     CV<C> acc_att, acc_bias;
     cv_zero(acc_att);
@@ -343,10 +343,11 @@ __global__ void __launch_bounds__(kSwThreads, 1) edge_bwd_sw_kernel(const SwArgs
         int stD = (svb + sg.dfirst * T) % Ps;          // stash row of the first node of the next D chunk
         int posS = (vbR + sw_wlo(sg.ca, R)) % P;       // ring row of the window start of the next S chunk
         int stS = (svb + sw_wlo(sg.ca, R)) % Ps;       // stash row of that window start
-        const uint32_t key = DROP ? (dropout_snapshot_key(seed, (uint32_t)sg.snap) ^ head_key) : 0u;
+        const DropKeys sk = DROP ? dropout_snapshot_keys(seed, (uint32_t)sg.snap) : DropKeys{0u, 0u};
         DropCfg<DROP> drop;
         drop.thr = a.drop_thr;
-        drop.key = key;
+        drop.key = sk.k1 ^ head_key.k1;
+        drop.key2 = sk.k2 ^ head_key.k2;
         drop.inv_keep = a.inv_keep;
         const int64_t snap0 = (int64_t)sg.snap * N;
         CV<C> xl_next;

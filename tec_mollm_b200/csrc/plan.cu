@@ -1,8 +1,8 @@
 // plan.cu -- one-time graph plan: what PyG redoes on every forward (remove_self_loops + add_self_loops,
 // boolean-mask nonzero with a device->host sync; GATv2Conv.forward called at
 // /root/reference/src/model/modules.py:356) becomes a cached, immutable structure:
-//   * destination-sorted CSR (stable: a destination's in-edges keep the input order, self loop last,
-//     i.e. exactly PyG's per-destination accumulation order on CPU),
+//   * destination-sorted CSR (stable: a destination's in-edges keep the input order; the self loop comes FIRST in every
+//     row -- its score is the softmax shift -- so the summation order is not PyG's: parity is to tolerance, not by order),
 //   * source-sorted CSR with, per out-slot, the in-CSR slot of the same edge (dropout counter),
 //   * per tile of `tile_nodes` consecutive nodes, the window [lo, hi) of rows the tile touches either as
 //     in-neighbours or out-neighbours -- the contiguous slab the edge kernels stage in shared memory.
@@ -140,7 +140,7 @@ static int build_tiling(tg_tiling &tl, bool bwd, int32_t T, int64_t N, const std
         tg_tile_meta &m = tl.h_meta[t];
         m.lo = l;
         m.hi = h + 1;
-        bool ok = (h + 1 - l) <= 65535 && kin <= 65535 && kout <= 65535;
+        bool ok = (h + 1 - l) <= 65535 && kin <= 32767 && kout <= 32767;  // kin | kout << 16 and deg = in | out << 16 live in signed int32
         if (ok && bwd) ok = int64_t(rp_in[h + 1]) - rp_in[l] <= 65535;  // relative dropout slots fit uint16
         m.eligible = ok ? 1 : 0;
         m.kin_kout = ok ? (kin | (kout << 16)) : 0;
@@ -424,7 +424,7 @@ extern "C" int tecgat_dropout_mask_host(uint64_t seed, int64_t first_slot, int64
         const int64_t g = first_slot + i;
         const uint32_t snap = uint32_t(g / edges_per_snapshot), slot = uint32_t(g % edges_per_snapshot);
         for (int32_t h = 0; h < heads; ++h)
-            keep[i * heads + h] = tg::dropout_bits(tg::dropout_key(seed, snap, uint32_t(h)), slot) >= thr;
+            keep[i * heads + h] = tg::dropout_bits(tg::dropout_keys(seed, snap, uint32_t(h)), slot) >= thr;
     }
     return TECGAT_OK;
 }

@@ -78,6 +78,31 @@ def test_dropout_mask_host_statistics(lib):
     assert abs(both.mean() - p * p) < 2e-3
 
 
+def test_dropout_streams_are_not_shifted_copies(lib):
+    """with one 32-bit key per (snapshot, head) stream, two streams whose keys differ by a multiple of the counter
+    stride were the SAME mask sequence shifted by a few slots.  The second key perturbs the finishing function: no stream equals a
+    shifted copy of another, and the agreement of any two streams at small shifts is what independent draws give; the high half
+    of the 64-bit seed matters."""
+    from tec_mollm_b200 import _lib
+
+    E, S, H, p = 4096, 96, 2, 0.25
+    keep = np.empty((S * E, H), dtype=np.uint8)
+    _lib.call("tecgat_dropout_mask_host", C.c_uint64(0xDEADBEEF12345678), 0, S * E, H, C.c_float(p), E, C.c_void_p(keep.ctypes.data))
+    streams = keep.reshape(S, E, H).transpose(0, 2, 1).reshape(S * H, E).astype(np.int8)
+    assert len({s.tobytes() for s in streams}) == S * H                 # all distinct
+    expect = p * p + (1 - p) * (1 - p)                                   # P(two independent keep bits agree)
+    a = streams[:48]
+    worst = 0.0
+    for shift in range(0, 9):
+        b = streams[48:96, shift:]
+        agree = (a[:, None, : E - shift] == b[None, :, :]).mean(axis=2)   # (48, 48) stream pairs
+        worst = max(worst, float(np.abs(agree - expect).max()))
+    assert worst < 0.05, worst                                           # a shifted copy would agree ~100 %
+    hi = np.empty((E, H), dtype=np.uint8)
+    _lib.call("tecgat_dropout_mask_host", C.c_uint64(0x0000000012345678), 0, E, H, C.c_float(p), E, C.c_void_p(hi.ctypes.data))
+    assert (hi != keep[:E]).mean() > 0.2
+
+
 def test_errors_are_reported_not_thrown(lib):
     from tec_mollm_b200 import _lib
 
