@@ -279,12 +279,13 @@ __device__ __forceinline__ void st_elem(float *p, float v) { *p = v; }
 __device__ __forceinline__ void st_elem(__nv_bfloat16 *p, float v) { *p = __float2bfloat16_rn(v); }
 
 // ---- counter-based dropout RNG: integer-only, restated on the host (tecgat_dropout_mask_host) -----------------
-// keep(seed, snapshot, CSR slot, head).  The 64-bit seed, the snapshot and the head are folded ONCE per (item, lane)
-// into TWO well-mixed 32-bit keys; per edge one multiply-add, one xor-shift (3-input xor with the second key) and one
-// multiply produce 32 uniform bits that are compared against round(p * 2^32):  6 integer instructions per (edge, head).
-// key1 selects the starting point of the counter sequence, key2 perturbs the finishing function: two (snapshot, head) streams
-// whose key1 happen to differ by a multiple of kDropMul would otherwise be SHIFTED COPIES of one mask sequence;
-// together the keys carry 64 bits of the seed.
+// keep(seed, snapshot, head, CSR slot).  Every draw of one launch has its OWN 32-bit counter
+//     n = (snapshot * heads + head) * edges_per_snapshot + slot
+// (unique while snapshots * heads * edges <= 2^32: 2.9e8 at B = 128 on the 2911-node graph), so no two (snapshot, head)
+// streams can be shifted copies of one another.  h = n * kDropMul + base(seed) is a Weyl sequence whose start
+// mixes all 64 seed bits; one xor-shift and one multiply finish it into 32 uniform bits that are compared against
+// round(p * 2^32).  Per (item, lane) the kernels form key = base + stream * (edges * kDropMul) once; per edge they spend one
+// add (h advances by kDropMul), one shift, one xor, one multiply, one compare, one select.
 __host__ __device__ __forceinline__ uint32_t fmix32(uint32_t h) {
     h ^= h >> 16;
     h *= 0x85EBCA6Bu;
@@ -293,34 +294,26 @@ __host__ __device__ __forceinline__ uint32_t fmix32(uint32_t h) {
     h ^= h >> 16;
     return h;
 }
-struct DropKeys {
-    uint32_t k1, k2;
-};
-__host__ __device__ __forceinline__ DropKeys dropout_snapshot_keys(uint64_t seed, uint32_t snapshot) {  // once per snapshot
-    const uint32_t lo = static_cast<uint32_t>(seed), hi = static_cast<uint32_t>(seed >> 32);
-    DropKeys k;
-    k.k1 = fmix32(lo ^ fmix32(hi + 0x9E3779B9u * (snapshot + 1u)));
-    k.k2 = fmix32(hi ^ fmix32(lo + 0x85EBCA77u * (snapshot + 0x632BE5ABu)));
-    return k;
-}
-__host__ __device__ __forceinline__ DropKeys dropout_head_keys(uint32_t head) {  // once per lane
-    DropKeys k;
-    k.k1 = fmix32(0x7FEB352Du * (head + 1u));
-    k.k2 = fmix32(0x846CA68Bu * (head + 0x9E3779B9u));
-    return k;
-}
-__host__ __device__ __forceinline__ DropKeys dropout_keys(uint64_t seed, uint32_t snapshot, uint32_t head) {
-    const DropKeys a = dropout_snapshot_keys(seed, snapshot), b = dropout_head_keys(head);
-    return DropKeys{a.k1 ^ b.k1, a.k2 ^ b.k2};
-}
 constexpr uint32_t kDropMul = 0x9E3779B1u;
-// second half of the hash; `h` = slot * kDropMul + key1 (consecutive slots: h advances by kDropMul, one integer add)
-__host__ __device__ __forceinline__ uint32_t dropout_finish(uint32_t h, uint32_t key2) {
-    h = h ^ (h >> 15) ^ key2;
+__host__ __device__ __forceinline__ uint32_t dropout_base(uint64_t seed) {  // once per thread
+    const uint32_t lo = static_cast<uint32_t>(seed), hi = static_cast<uint32_t>(seed >> 32);
+    return fmix32(lo ^ fmix32(hi + 0x9E3779B9u));
+}
+// stream_stride = edges_per_snapshot * kDropMul (mod 2^32): the counter distance between consecutive (snapshot, head) streams
+__host__ __device__ __forceinline__ uint32_t dropout_stream_stride(int64_t edges_per_snapshot) {
+    return static_cast<uint32_t>(static_cast<uint64_t>(edges_per_snapshot)) * kDropMul;
+}
+__host__ __device__ __forceinline__ uint32_t dropout_key(uint32_t base, uint32_t snapshot, uint32_t heads, uint32_t head,
+                                                         uint32_t stream_stride) {  // once per (snapshot, lane)
+    return base + (snapshot * heads + head) * stream_stride;
+}
+// second half of the hash; `h` = slot * kDropMul + key (consecutive slots: h advances by kDropMul, one integer add)
+__host__ __device__ __forceinline__ uint32_t dropout_finish(uint32_t h) {
+    h ^= h >> 15;
     h *= 0x85EBCA6Bu;
     return h;
 }
-__host__ __device__ __forceinline__ uint32_t dropout_bits(DropKeys key, uint32_t slot) { return dropout_finish(slot * kDropMul + key.k1, key.k2); }
+__host__ __device__ __forceinline__ uint32_t dropout_bits(uint32_t key, uint32_t slot) { return dropout_finish(slot * kDropMul + key); }
 __host__ __device__ __forceinline__ uint32_t dropout_threshold(float p) {
     // keep iff bits >= thr;  P(drop) = thr / 2^32
     double t = static_cast<double>(p) * 4294967296.0;

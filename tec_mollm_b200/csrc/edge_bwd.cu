@@ -34,6 +34,7 @@ struct EdgeBwdArgs {
     int32_t N, T, num_tiles, S, H, npw;
     float slope, inv_keep;
     uint32_t drop_thr;
+    uint32_t stream_stride;  // dropout counter distance between consecutive (snapshot, head) streams
     uint64_t seed;
     const uint64_t *seed_dev;  // non-NULL: the seed lives in device memory (the one the forward used)
     int32_t literal;
@@ -312,10 +313,9 @@ __global__ void __launch_bounds__(WG ? 384 : 256, 1) edge_bwd_kernel(const EdgeB
     cv_load_param<C>(attm, a.att + hh * C, par, 0.5f * (1.f - a.slope) * kLog2e);
     cv_load_param<C>(att_h, a.att + hh * C, par, 1.f);
     cv_load_param<C>(bias_h, a.bias + hh * C, par, 1.f);
-    const DropKeys head_key = dropout_head_keys((uint32_t)hh);
-    uint32_t key = 0, key2 = 0;
+    uint32_t key = 0;
     int key_snap = -1;
-    const uint64_t seed = (DROP && a.seed_dev) ? __ldg(a.seed_dev) : a.seed;
+    const uint32_t drop_base = dropout_base((DROP && a.seed_dev) ? __ldg(a.seed_dev) : a.seed);
     // per-lane fp32 partial sums of d att and d bias: one term per item, flushed to a CTA partial row every kFlushItems
     // items (the second stage sums all rows in fp64)
     CV<C> acc_att, acc_bias;
@@ -365,15 +365,12 @@ __global__ void __launch_bounds__(WG ? 384 : 256, 1) edge_bwd_kernel(const EdgeB
         const bool active = head_ok && node_l < nt;
         const int64_t row = (int64_t)snap * N + n0 + node_l;
         if (DROP && a.drop_thr && snap != key_snap) {
-            const DropKeys sk = dropout_snapshot_keys(seed, (uint32_t)snap);
-            key = sk.k1 ^ head_key.k1;
-            key2 = sk.k2 ^ head_key.k2;
+            key = dropout_key(drop_base, (uint32_t)snap, (uint32_t)H, (uint32_t)hh, a.stream_stride);
             key_snap = snap;
         }
         DropCfg<DROP> drop;
         drop.thr = a.drop_thr;
         drop.key = key;
-        drop.key2 = key2;
         drop.inv_keep = a.inv_keep;
         CV<C> dxl, dxr, tatt, g_v;
         if (staged) {
@@ -792,6 +789,7 @@ int tg::edge_bwd_run(const tecgat_plan_t *plan, const void *xl, const void *xr, 
     a.slope = negative_slope;
     a.drop_thr = dropout_p > 0.f ? std::max(1u, dropout_threshold(dropout_p)) : 0u;
     a.inv_keep = 1.f / (1.f - dropout_p);
+    a.stream_stride = dropout_stream_stride(plan->num_edges);
     a.seed = seed;
     a.seed_dev = seed_dev;
     a.literal = (mode == TECGAT_MODE_LITERAL);

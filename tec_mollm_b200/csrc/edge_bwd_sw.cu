@@ -33,6 +33,7 @@ struct SwArgs {
     int32_t slabD_bytes, slabS_bytes, stash_stride;
     float slope, inv_keep;
     uint32_t drop_thr;
+    uint32_t stream_stride;  // dropout counter distance between consecutive (snapshot, head) streams
     uint64_t seed;
     const uint64_t *seed_dev;
     int32_t P, Ps;  // ring capacities: rows (xl / xr / g), nodes (stash)
@@ -267,8 +268,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) edge_bwd_sw_kernel(const SwArgs
     }
     bar_sync_named(kBarConsumers, nct);
     const float *att_s = prm + h * C, *nbias_s = prm + HC + h * C;
-    const DropKeys head_key = dropout_head_keys((uint32_t)h);
-    const uint64_t seed = (DROP && a.seed_dev) ? __ldg(a.seed_dev) : a.seed;
+    const uint32_t drop_base = dropout_base((DROP && a.seed_dev) ? __ldg(a.seed_dev) : a.seed);
     CV<C> acc_att, acc_bias;
     cv_zero(acc_att);
     cv_zero(acc_bias);
@@ -343,11 +343,9 @@ __global__ void __launch_bounds__(kSwThreads, 1) edge_bwd_sw_kernel(const SwArgs
         int stD = (svb + sg.dfirst * T) % Ps;          // stash row of the first node of the next D chunk
         int posS = (vbR + sw_wlo(sg.ca, R)) % P;       // ring row of the window start of the next S chunk
         int stS = (svb + sw_wlo(sg.ca, R)) % Ps;       // stash row of that window start
-        const DropKeys sk = DROP ? dropout_snapshot_keys(seed, (uint32_t)sg.snap) : DropKeys{0u, 0u};
         DropCfg<DROP> drop;
         drop.thr = a.drop_thr;
-        drop.key = sk.k1 ^ head_key.k1;
-        drop.key2 = sk.k2 ^ head_key.k2;
+        drop.key = dropout_key(drop_base, (uint32_t)sg.snap, (uint32_t)H, (uint32_t)h, a.stream_stride);
         drop.inv_keep = a.inv_keep;
         const int64_t snap0 = (int64_t)sg.snap * N;
         CV<C> xl_next;
@@ -684,6 +682,7 @@ int edge_bwd_sw_try(const tecgat_plan_t *plan, const void *xl, const void *xr, c
     a.kinp = sw->kinp; a.koutp = sw->koutp;
     a.slabD_bytes = sw->slabD_bytes; a.slabS_bytes = sw->slabS_bytes; a.stash_stride = sw->stash_stride;
     a.slope = negative_slope; a.inv_keep = 1.f / (1.f - dropout_p); a.drop_thr = drop_thr; a.seed = seed; a.seed_dev = seed_dev;
+    a.stream_stride = dropout_stream_stride(plan->num_edges);
     a.max_flushes = max_flushes;
     a.chunks = int64_t(sw->J) * snapshots;
     if (out_channels == 11)

@@ -266,13 +266,13 @@ __device__ __forceinline__ void cv_axpy(CV<C> &y, float a, const CV<C> &x) {
 
 template <bool DROP>  // DROP = false: inference / p = 0 instantiation without the hash
 struct DropCfg {
-    uint32_t thr, key, key2;
+    uint32_t thr, key;
     float inv_keep;
     __device__ __forceinline__ float q(uint32_t slot) const { return qh(slot * kDropMul + key); }
     __device__ __forceinline__ float qh(uint32_t h) const {  // h = slot * kDropMul + key (consecutive slots: one add)
         if (!DROP) return 1.f;
         // no branch on "dropout off": threshold 0 keeps every edge and inv_keep is 1 (the loop bodies stay one basic block)
-        return dropout_finish(h, key2) >= thr ? inv_keep : 0.f;
+        return dropout_finish(h) >= thr ? inv_keep : 0.f;
     }
 };
 

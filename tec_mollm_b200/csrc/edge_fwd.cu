@@ -28,6 +28,7 @@ struct EdgeFwdArgs {
     int32_t N, T, num_tiles, S, H, npw;
     float slope, inv_keep;
     uint32_t drop_thr;
+    uint32_t stream_stride;  // dropout counter distance between consecutive (snapshot, head) streams
     uint64_t seed;
     const uint64_t *seed_dev;  // non-NULL: the seed lives in device memory (CUDA-graph replays draw fresh masks)
     int32_t literal;
@@ -47,7 +48,7 @@ __device__ __forceinline__ void fwd_lane(const int Ts /* slab row stride */, con
                                          const ST *xr_chunk, const ST *xl_self /* own row, + h*C */,
                                          const ST *xl_lane /* window row 0 (FAST) or snapshot row 0, + h*C */, int HC, int par,
                                          const uint16_t *ell /* + node_l */, const int32_t *col /* + k0 */, int deg, int kmax_w,
-                                         uint32_t slot0, uint32_t key, uint32_t key2, CV<C> &out, float &stat) {
+                                         uint32_t slot0, uint32_t key, CV<C> &out, float &stat) {
     CV<C> xr_i, xl_i, acc;
     if (deg > 0) {
         cv_load<C, VEC>(xr_i, xr_chunk, par);
@@ -72,7 +73,7 @@ __device__ __forceinline__ void fwd_lane(const int Ts /* slab row stride */, con
         if (!DROP) return w;  // inference / p = 0 instantiation: no hash
         // no branch on "dropout off": threshold 0 keeps every edge and inv_keep is 1, so the loop body stays ONE basic
         // block and the two edges of an iteration interleave freely
-        return dropout_finish(hk, key2) >= a.drop_thr ? w * a.inv_keep : 0.f;
+        return dropout_finish(hk) >= a.drop_thr ? w * a.inv_keep : 0.f;
     };
 #pragma unroll 1
     for (int attempt = 0; attempt < 2; ++attempt) {
@@ -204,10 +205,9 @@ __global__ void __launch_bounds__(512, 1) edge_fwd_kernel(const EdgeFwdArgs a) {
     cv_load_param<C>(attm, a.att + hh * C, par, 0.5f * (1.f - a.slope) * kLog2e);
     const float *bias_h = a.bias + hh * C;
     float *ybuf = reinterpret_cast<float *>(smem + a.off_y) + warp * npw * HC;
-    const DropKeys head_key = dropout_head_keys((uint32_t)hh);
-    uint32_t key = 0, key2 = 0;
+    uint32_t key = 0;
     int key_snap = -1;
-    const uint64_t seed = (DROP && a.seed_dev) ? __ldg(a.seed_dev) : a.seed;
+    const uint32_t drop_base = dropout_base((DROP && a.seed_dev) ? __ldg(a.seed_dev) : a.seed);
 
     for (int w = 0; w < n_items; ++w) {
         const tg_tile_meta m = load_meta(meta_s, a.meta, a.num_tiles, tile);
@@ -218,9 +218,7 @@ __global__ void __launch_bounds__(512, 1) edge_fwd_kernel(const EdgeFwdArgs a) {
         const bool active = head_ok && node_l < nt;
         const int64_t row = (int64_t)snap * N + n0 + node_l;
         if (DROP && a.drop_thr && snap != key_snap) {
-            const DropKeys sk = dropout_snapshot_keys(seed, (uint32_t)snap);
-            key = sk.k1 ^ head_key.k1;
-            key2 = sk.k2 ^ head_key.k2;
+            key = dropout_key(drop_base, (uint32_t)snap, (uint32_t)H, (uint32_t)hh, a.stream_stride);
             key_snap = snap;
         }
         CV<C> out;
@@ -238,7 +236,7 @@ __global__ void __launch_bounds__(512, 1) edge_fwd_kernel(const EdgeFwdArgs a) {
             const uint32_t slot0 = active ? (uint32_t)k0s[node_l] : 0u;
             const int kmax_w = __reduce_max_sync(0xFFFFFFFFu, deg);
             fwd_lane<C, ST, VEC, true, DROP>(Ts, a, attp, attm, bias_h, xr_s + node_l * HC + hh * C, xl_s + (n0 + node_l - lo) * HC + hh * C,
-                                       xl_s + hh * C, HC, par, ell, nullptr, deg, kmax_w, slot0, key, key2, out, stat);
+                                       xl_s + hh * C, HC, par, ell, nullptr, deg, kmax_w, slot0, key, out, stat);
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[ring.st]);  // this warp no longer reads the stage
             ring.advance(NS);
@@ -274,7 +272,7 @@ __global__ void __launch_bounds__(512, 1) edge_fwd_kernel(const EdgeFwdArgs a) {
             const ST *xl_snap = static_cast<const ST *>(a.xl) + (int64_t)snap * N * HC + hh * C;
             const ST *xr_chunk = static_cast<const ST *>(a.xr) + row * HC + hh * C;
             fwd_lane<C, ST, VEC, false, DROP>(Ts, a, attp, attm, bias_h, xr_chunk, xl_snap + (int64_t)(n0 + node_l) * HC, xl_snap, HC, par, nullptr,
-                                        a.col + k0, deg, kmax_w, (uint32_t)k0, key, key2, out, stat);
+                                        a.col + k0, deg, kmax_w, (uint32_t)k0, key, out, stat);
             if (active) cv_store<C, VEC>(a.y + row * HC + hh * C, out, par);
         }
         if (active) a.stat[row * H + hh] = stat;
@@ -448,6 +446,7 @@ int tg::edge_fwd_run(const tecgat_plan_t *plan, const void *xl, const void *xr, 
     a.slope = negative_slope;
     a.drop_thr = dropout_p > 0.f ? std::max(1u, dropout_threshold(dropout_p)) : 0u;
     a.inv_keep = 1.f / (1.f - dropout_p);
+    a.stream_stride = dropout_stream_stride(plan->num_edges);
     a.seed = seed;
     a.seed_dev = seed_dev;
     a.literal = (mode == TECGAT_MODE_LITERAL);

@@ -49,6 +49,45 @@ __global__ void __launch_bounds__(kEmbThreads) embed_fwd_kernel(const float *__r
     }
 }
 
+// Same pass for even channel counts known at compile time (the reference's 6 raw + 16 embedding channels): one float2 per
+// thread and iteration, the row / channel split is a division by a constant.  Bit-identical to the kernel above (same adds).
+template <int CR2, int DE2>
+__global__ void __launch_bounds__(kEmbThreads) embed_fwd_pairs_kernel(const float2 *__restrict__ x, const int32_t *__restrict__ tf,
+                                                                      const float2 *__restrict__ node, const float *__restrict__ tod,
+                                                                      const float *__restrict__ doy, const float *__restrict__ year,
+                                                                      const float *__restrict__ season, float2 *__restrict__ out, int N,
+                                                                      int n_tod, int n_doy, int n_year, int n_season, int nodes_per_block) {
+    constexpr int F2 = CR2 + DE2, De = 2 * DE2;
+    __shared__ float2 T2[DE2];
+    const int s = blockIdx.y;
+    const int n0 = blockIdx.x * nodes_per_block;
+    const int nn = min(nodes_per_block, N - n0);
+    if ((int)threadIdx.x < De) {
+        const int c = threadIdx.x;
+        auto clampi = [](int v, int hi) { return v < 0 ? 0 : (v >= hi ? hi - 1 : v); };
+        const int i0 = clampi(tf[s * 4 + 0], n_tod), i1 = clampi(tf[s * 4 + 1], n_doy), i2 = clampi(tf[s * 4 + 2], n_year),
+                  i3 = clampi(tf[s * 4 + 3], n_season);
+        reinterpret_cast<float *>(T2)[c] =
+            __fadd_rn(__fadd_rn(__fadd_rn(tod[i0 * De + c], doy[i1 * De + c]), year[i2 * De + c]), season[i3 * De + c]);
+    }
+    __syncthreads();
+    const int64_t row0 = (int64_t)s * N + n0;
+    const float2 *xs = x + row0 * CR2;
+    const float2 *ns = node + (int64_t)n0 * DE2;
+    float2 *os = out + row0 * F2;
+    for (int i = threadIdx.x; i < nn * F2; i += kEmbThreads) {
+        const int n = i / F2, c = i - n * F2;
+        float2 v;
+        if (c < CR2) {
+            v = __ldcs(xs + n * CR2 + c);  // read once
+        } else {
+            const float2 e = __ldg(ns + n * DE2 + (c - CR2)), t = T2[c - CR2];
+            v = make_float2(__fadd_rn(e.x, t.x), __fadd_rn(e.y, t.y));
+        }
+        os[i] = v;
+    }
+}
+
 // ---- backward ------------------------------------------------------------------------------------------------------
 // One warp owns (a tile of 128 nodes, a group of snapshots).  Lane = (row r = lane / 8, channel pair k = lane % 8): one load
 // instruction covers four rows' contiguous 64-byte embedding halves.  For De != 16 the generic scalar path below is used.
@@ -163,9 +202,15 @@ extern "C" int tecgat_embed_fwd(const float *x_dev, const int32_t *tf_dev, const
     TG_REQUIRE(snapshots <= 65535, TECGAT_ENOSUP, "embed_fwd: more than 65535 snapshots per call");
     const int npb = 128;
     dim3 grid((nodes + npb - 1) / npb, snapshots);
-    embed_fwd_kernel<<<grid, kEmbThreads, 0, static_cast<cudaStream_t>(stream)>>>(x_dev, tf_dev, node_dev, tod_dev, doy_dev, year_dev, season_dev,
-                                                                              out_dev, nodes, raw_channels, emb_dim, n_tod, n_doy,
-                                                                              n_year, n_season, npb);
+    const bool aligned8 = ((reinterpret_cast<uintptr_t>(x_dev) | reinterpret_cast<uintptr_t>(node_dev) | reinterpret_cast<uintptr_t>(out_dev)) & 7) == 0;
+    if (raw_channels == 6 && emb_dim == 16 && aligned8)  // the reference's shape (modules.py:211-266 with d_emb = 16)
+        embed_fwd_pairs_kernel<3, 8><<<grid, kEmbThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+            reinterpret_cast<const float2 *>(x_dev), tf_dev, reinterpret_cast<const float2 *>(node_dev), tod_dev, doy_dev, year_dev,
+            season_dev, reinterpret_cast<float2 *>(out_dev), nodes, n_tod, n_doy, n_year, n_season, npb);
+    else
+        embed_fwd_kernel<<<grid, kEmbThreads, 0, static_cast<cudaStream_t>(stream)>>>(x_dev, tf_dev, node_dev, tod_dev, doy_dev, year_dev, season_dev,
+                                                                                  out_dev, nodes, raw_channels, emb_dim, n_tod, n_doy,
+                                                                                  n_year, n_season, npb);
     tg_count_launch();
     TG_LAUNCH_CHECK();
     return TECGAT_OK;

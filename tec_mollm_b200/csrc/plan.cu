@@ -420,11 +420,12 @@ extern "C" int tecgat_dropout_mask_host(uint64_t seed, int64_t first_slot, int64
     // slot = snapshot * edges_per_snapshot + CSR slot (the kernels' numbering)
     TG_REQUIRE(keep && heads > 0 && count >= 0 && edges_per_snapshot > 0, TECGAT_EINVAL, "dropout_mask_host: bad argument");
     const uint32_t thr = tg::dropout_threshold(dropout_p);
+    const uint32_t base = tg::dropout_base(seed), stride = tg::dropout_stream_stride(edges_per_snapshot);
     for (int64_t i = 0; i < count; ++i) {
         const int64_t g = first_slot + i;
         const uint32_t snap = uint32_t(g / edges_per_snapshot), slot = uint32_t(g % edges_per_snapshot);
         for (int32_t h = 0; h < heads; ++h)
-            keep[i * heads + h] = tg::dropout_bits(tg::dropout_keys(seed, snap, uint32_t(h)), slot) >= thr;
+            keep[i * heads + h] = tg::dropout_bits(tg::dropout_key(base, snap, uint32_t(heads), uint32_t(h), stride), slot) >= thr;
     }
     return TECGAT_OK;
 }

@@ -80,8 +80,9 @@ def test_dropout_mask_host_statistics(lib):
 
 def test_dropout_streams_are_not_shifted_copies(lib):
     """with one 32-bit key per (snapshot, head) stream, two streams whose keys differ by a multiple of the counter
-    stride were the SAME mask sequence shifted by a few slots.  The second key perturbs the finishing function: no stream equals a
-    shifted copy of another, and the agreement of any two streams at small shifts is what independent draws give; the high half
+    stride were the SAME mask sequence shifted by a few slots.  Every draw of a launch now has its own counter
+    ((snapshot * heads + head) * edges + slot): no stream equals a shifted copy of another, and the agreement of any two streams at
+    small shifts is what independent draws give; the high half
     of the 64-bit seed matters."""
     from tec_mollm_b200 import _lib
 

@@ -40,6 +40,30 @@ def test_embedding_matches_the_reference_class(cuda_device):
         emb(x.cpu(), tf.cpu())
 
 
+@pytest.mark.parametrize("raw_channels", [6, 4, 5])
+def test_embedding_forward_other_channel_counts(cuda_device, raw_channels):
+    """The reference's shape (6 raw channels) takes the float2 kernel, anything else the scalar one: both must be the
+    reference's op sequence (modules.py:259-264) bit for bit, including an unaligned (odd-offset) input view."""
+    from tec_mollm_b200 import SpatioTemporalEmbedding
+
+    B, L, N = 2, 5, 301
+    torch.manual_seed(11)
+    emb = SpatioTemporalEmbedding(16, num_nodes=N).to(cuda_device)
+    buf = torch.randn(B * L * N * raw_channels + 1, device=cuda_device)
+    tf = torch.stack([torch.randint(0, 12, (B, L)), torch.randint(0, 366, (B, L)), torch.randint(0, 13, (B, L)),
+                      torch.randint(0, 4, (B, L))], dim=-1).float().to(cuda_device)
+    idx = tf.long()
+    for off in (0, 1):  # off = 1: a 4-byte-aligned view (the float2 kernel must not be chosen for it)
+        x = buf[off:off + B * L * N * raw_channels].view(B, L, N, raw_channels)
+        with torch.no_grad():
+            t = (emb.tod_embedding(idx[..., 0]) + emb.doy_embedding(idx[..., 1]) + emb.year_embedding(idx[..., 2])
+                 + emb.season_embedding(idx[..., 3]))
+            node = emb.node_embedding(torch.arange(N, device=cuda_device))
+            ref = torch.cat([x, node.view(1, 1, N, 16) + t.unsqueeze(2)], dim=-1)
+            out = emb(x, tf)
+        assert torch.equal(out, ref)
+
+
 def test_embedding_backward_is_deterministic_and_accumulates_over_snapshots(cuda_device):
     """Full-size rows (2911 nodes, 96 snapshots): gradients against torch's own embedding autograd, and bit-reproducible."""
     from tec_mollm_b200 import SpatioTemporalEmbedding
