@@ -31,7 +31,12 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)  # the handle without building a Stream object (~10x cheaper)
+
+
 def _stream(device: torch.device):
+    if _raw_stream is not None and device.index is not None:
+        return C.c_void_p(_raw_stream(device.index))
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
