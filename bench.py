@@ -591,6 +591,15 @@ def other_configs(enc, flat, ei, args, dev, E, cfg, N, x, gy):
     ms, _ = timed(make(x, gy, other), 5)
     out["bf16_autocast" if other else "fp32"] = {"batch_per_gpu": x.size(0) // L_IN, "ms_per_step": ms,
                                                   "edge_msgs_per_s": x.size(0) * E / (ms * 1e-3)}
+    # "dropout 0 for parity, 0.1 for timing realism (report both)" -- the same step with the p = 0 kernels
+    p_saved = enc.gat_conv.dropout
+    try:
+        enc.gat_conv.dropout = 0.0
+        ms, _ = timed(make(x, gy, args.autocast), 5)
+        out["dropout_0"] = {"batch_per_gpu": x.size(0) // L_IN, "ms_per_step": ms, "edge_msgs_per_s": x.size(0) * E / (ms * 1e-3),
+                            "note": "training mode with attention dropout p = 0 (the headline runs the reference's p = 0.1)"}
+    finally:
+        enc.gat_conv.dropout = p_saved
     S2 = 2 * L_IN
     x2 = torch.randn(S2, N, F_IN, device=dev).requires_grad_(True)
     g2 = torch.randn(S2, N, HC, device=dev)
