@@ -316,12 +316,13 @@ class GATv2Conv(nn.Module):
             self.bias.zero_()
 
     # ---- plan cache: the reference passes the same edge_index tensor every step (train.py:292-294, 388) ----
-    def plan_for(self, edge_index: torch.Tensor, num_nodes: int) -> GraphPlan:
-        key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape), int(num_nodes), edge_index.device)
+    def plan_for(self, edge_index: torch.Tensor, num_nodes: int, tiles: Optional[Tuple[int, int]] = None) -> GraphPlan:
+        tiles = tiles or (self._tile_nodes, self._tile_nodes_bwd)
+        key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape), int(num_nodes), edge_index.device, tiles)
         hit = self._plans.get(key)
         if hit is not None:
             return hit[0]
-        plan = GraphPlan(edge_index, num_nodes, self._tile_nodes, self._tile_nodes_bwd)
+        plan = GraphPlan(edge_index, num_nodes, tiles[0], tiles[1])
         if len(self._plans) >= 8:
             self._plans.pop(next(iter(self._plans)))
         self._plans[key] = (plan, edge_index)  # keep the tensor alive so its data_ptr cannot be recycled
@@ -359,20 +360,52 @@ class GATv2Conv(nn.Module):
         x = x.contiguous()
         if x.dtype != torch.float32:
             x = x.float()
-        plan = self.plan_for(edge_index, num_nodes)
         p = self.dropout if self.training else 0.0
+        mode = _lib.MODE_SHARED if snapshot_mode == "shared" else _lib.MODE_LITERAL
+        if block is None and seed is None and self._split_head_pairs():
+            return self._forward_head_pairs(x, edge_index, int(snapshots), num_nodes, float(p), mode, dtype)
+        plan = self.plan_for(edge_index, num_nodes)
         seed_t = None
         if p > 0.0 and seed is None:  # an explicit ``seed`` (tests: reproduce the mask on the host) is passed by value
             seed_t = torch.empty(1, dtype=torch.int64, device=x.device)
             with _on_device(x.device):
                 _lib.call("tecgat_seed_advance", _ptr(self._dropout_state(x.device)), _ptr(seed_t), _stream(x.device))
             self._last_seed = seed_t  # tests rebuild the kernels' mask on the host from it
-        mode = _lib.MODE_SHARED if snapshot_mode == "shared" else _lib.MODE_LITERAL
         f32 = lambda t: t if t.dtype == torch.float32 else t.float()
         return _GATv2Function.apply(
             x, f32(self.lin_l.weight), f32(self.lin_l.bias), f32(self.lin_r.weight), f32(self.lin_r.bias),
             f32(self.att), f32(self.bias), plan, int(snapshots), self.heads, self.out_channels,
             self.negative_slope, float(p), int(seed or 0), seed_t, mode, dtype, _proj_impl(), block, self)
+
+    # ---- more than two heads: the heads of a GATv2 layer only meet in the concatenation, so H heads = H / 2 independent
+    # two-head layers on slices of the parameters.  Rows of 2 * C channels fit the fully staged edge kernels where H * C
+    # channels do not (BASELINE config 4: H = 4, C = 11 -- the backward's three 176-byte row windows exceed shared memory and
+    # it gathers rows from L2 instead), and the two-head shapes are the ones compiled with fixed tile sizes.
+    def _split_head_pairs(self) -> bool:
+        knob = os.environ.get("TECGAT_HEAD_SPLIT")  # tests: "0" keeps the one-launch kernels for any head count
+        if knob is not None:
+            return knob != "0" and self.heads > 2 and self.heads % 2 == 0
+        return self.heads > 2 and self.heads % 2 == 0 and self.out_channels in (5, 11)
+
+    def _forward_head_pairs(self, x, edge_index, snapshots, num_nodes, p, mode, dtype):
+        C2 = 2 * self.out_channels
+        plan = self.plan_for(edge_index, num_nodes, (tile_nodes_for(2), tile_nodes_for(2, backward=True, out_channels=self.out_channels)))
+        f32 = lambda t: t if t.dtype == torch.float32 else t.float()
+        wl, bl, wr, br = f32(self.lin_l.weight), f32(self.lin_l.bias), f32(self.lin_r.weight), f32(self.lin_r.bias)
+        att, bias = f32(self.att), f32(self.bias)
+        ys = []
+        for g in range(self.heads // 2):
+            sl = slice(g * C2, (g + 1) * C2)
+            seed_t = None
+            if p > 0.0:  # every pair draws its own seed: the kernels number the (snapshot, head) streams inside one call
+                seed_t = torch.empty(1, dtype=torch.int64, device=x.device)
+                with _on_device(x.device):
+                    _lib.call("tecgat_seed_advance", _ptr(self._dropout_state(x.device)), _ptr(seed_t), _stream(x.device))
+            al = lambda t: t if t.data_ptr() % 16 == 0 else t.clone()  # parameter slices start 88 bytes into their tensors
+            ys.append(_GATv2Function.apply(x, al(wl[sl]), al(bl[sl]), al(wr[sl]), al(br[sl]), al(att[:, 2 * g:2 * g + 2]), al(bias[sl]),
+                                           plan, snapshots, 2, self.out_channels, self.negative_slope, p, 0, seed_t, mode, dtype,
+                                           _proj_impl(), None, None))
+        return torch.cat(ys, dim=1)
 
     def forward(self, x: torch.Tensor, edge_index: torch.Tensor, edge_attr=None, return_attention_weights=None):
         """PyG semantics for one 2-D input: ``num_nodes = x.size(0)`` rows, edges as given (so calling it the way

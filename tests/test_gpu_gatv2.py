@@ -293,8 +293,11 @@ def test_reference_graph_fp32_and_determinism(cuda_device):
         assert torch.equal(grads[k], grads2[k]), k
 
 
-def test_dense_graph_four_heads(cuda_device):
-    """BASELINE config 4: 300 km graph (76,532 edges, max degree 38), H=4, C=11."""
+@pytest.mark.parametrize("split", ["0", "1"])
+def test_dense_graph_four_heads(cuda_device, monkeypatch, split):
+    """BASELINE config 4: 300 km graph (76,532 edges, max degree 38), H=4, C=11 -- through the one-launch four-head kernels
+    (split = 0) and as two independent head pairs on parameter slices (the default for this shape)."""
+    monkeypatch.setenv("TECGAT_HEAD_SPLIT", split)
     g = load_golden("graph_cn300.npz")
     ei = torch.from_numpy(g["edge_index"])
     S, N, F, H, C = 2, 2911, 22, 4, 11
@@ -303,6 +306,41 @@ def test_dense_graph_four_heads(cuda_device):
     y, grads = _run_cuda(enc, x, ei, gy)
     y_ref, g_ref, _ = oracle_with_kernel_branches(x, ei, p, H, C, gy, cuda_device)
     _check(y, grads, y_ref, g_ref, TOL_F32, "cn300/h4")
+
+
+def test_head_pairs_training_and_autocast(cuda_device, monkeypatch):
+    """Four heads as two head pairs: dropout draws a different stream per pair (p -> 0 reproduces the deterministic result, the
+    two pairs' masks differ), bf16 autocast within 1e-2 of the fp32 path, literal mode equals the one-launch kernels."""
+    S, N, F, H, C = 3, 200, 22, 4, 11
+    ei = random_graph(N, 900, seed=41, isolated=(3,))
+    x, gy, p = _rand_case(S, N, F, H, C, seed=42, dtype=torch.float32)
+    outs = {}
+    for split in ("0", "1"):
+        monkeypatch.setenv("TECGAT_HEAD_SPLIT", split)
+        for mode in ("shared", "literal"):
+            enc = _encoder(F, H, C, p, cuda_device, mode=mode).eval()
+            outs[(split, mode)] = _run_cuda(enc, x, ei, gy)
+    for mode in ("shared", "literal"):
+        y0, g0 = outs[("0", mode)]
+        y1, g1 = outs[("1", mode)]
+        assert rel_err(y1, y0) <= 2e-6, mode
+        for k in g0:
+            assert rel_err(g1[k], g0[k]) <= 5e-6, (mode, k)
+    monkeypatch.setenv("TECGAT_HEAD_SPLIT", "1")
+    enc = _encoder(F, H, C, p, cuda_device, dropout=0.5).train()
+    xg = x.to(cuda_device)
+    with torch.no_grad():
+        ya, yb = enc(xg, ei.to(cuda_device)), enc(xg, ei.to(cuda_device))
+    assert not torch.equal(ya, yb)                                   # fresh masks per call
+    y_eval = outs[("1", "shared")][0]
+    d = (ya - y_eval).abs().reshape(S * N, 2, 2 * C).amax(dim=(0, 2))   # both pairs are perturbed by their own masks
+    assert (d > 1e-3).all()
+    enc = _encoder(F, H, C, p, cuda_device).eval()
+    y16, g16 = _run_cuda(enc, x, ei, gy, autocast=True)
+    assert rel_err(y16, y_eval) <= 1e-2
+    # bf16 gradients sit 5e-2 .. 7e-2 from fp64 in PyG's own autocast dtype flow too (test_gpu_round2's training-shape test gates
+    # them against that flow); here only that the pair path is not worse than that
+    assert rel_err(g16["x"], outs[("1", "shared")][1]["x"]) <= 1e-1
 
 
 @pytest.mark.parametrize("mode", ["shared", "literal"])
@@ -476,9 +514,10 @@ def test_four_dimensional_input_keeps_leading_dims(cuda_device):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("B,L,H,C", [(2, 3, 2, 11), (3, 48, 2, 11), (2, 5, 1, 3), (1, 4, 4, 11)])
-def test_forward_block_equals_the_reference_glue(cuda_device, B, L, H, C):
+def test_forward_block_equals_the_reference_glue(cuda_device, monkeypatch, B, L, H, C):
     """forward_block (fused residual + permute, tec_mollm.py:84-106) against the reference's own three lines run with
     torch ops around the same encoder: bit-identical output and input gradient, equal parameter gradients."""
+    monkeypatch.setenv("TECGAT_HEAD_SPLIT", "0")  # bit-identity holds between the SAME kernels (forward_block never splits head pairs)
     ei = torch.from_numpy(load_golden("graph_small150.npz")["edge_index"]).to(cuda_device)
     N = int(ei.max().item()) + 1
     F = H * C
