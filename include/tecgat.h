@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TECGAT_ABI_VERSION 3
+#define TECGAT_ABI_VERSION 4
 
 /* error codes */
 #define TECGAT_OK 0
@@ -134,6 +134,17 @@ int tecgat_forward(const tecgat_plan_t *plan, const float *x_dev, const float *w
                    int32_t in_channels, int32_t heads, int32_t out_channels, float negative_slope,
                    float dropout_p, uint64_t seed, const uint64_t *seed_dev, int32_t mode, int32_t dtype,
                    int32_t impl, void *stream);
+/* tecgat_forward that ALSO stores the output rows into a wider row-major tensor:
+ *   y_wide_dev[row * ld_wide + c] = y[row, c],  c < heads * out_channels
+ * (y_wide_dev points at the first column of this call's slice; 8-byte aligned, ld_wide even, in floats).  A layer with more
+ * than two heads runs as independent head pairs on parameter slices -- the heads of GATv2Conv (modules.py:329-336) only meet in
+ * the concatenation -- and each pair writes its columns of the (rows, H*C) result in place of a concatenation pass. */
+int tecgat_forward_into(const tecgat_plan_t *plan, const float *x_dev, const float *wl_dev, const float *bl_dev,
+                        const float *wr_dev, const float *br_dev, const float *att_dev, const float *bias_dev,
+                        void *xl_dev, void *xr_dev, float *y_dev, float *stat_dev, int32_t snapshots,
+                        int32_t in_channels, int32_t heads, int32_t out_channels, float negative_slope,
+                        float dropout_p, uint64_t seed, const uint64_t *seed_dev, int32_t mode, int32_t dtype,
+                        int32_t impl, float *y_wide_dev, int64_t ld_wide, void *stream);
 int64_t tecgat_backward_workspace(const tecgat_plan_t *plan, int32_t snapshots, int32_t in_channels,
                                   int32_t heads, int32_t out_channels, int32_t impl);
 int tecgat_backward_fused_supported(int32_t in_channels, int32_t hc, int32_t impl);

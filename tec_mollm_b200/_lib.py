@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libtecgat.so")
 F32, BF16 = 0, 1
 MODE_SHARED, MODE_LITERAL = 0, 1
 PROJ_TC, PROJ_FFMA = 0, 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _lock = threading.Lock()
 _lib = None
@@ -40,6 +40,7 @@ _SIGNATURES = {
     "tecgat_edge_bwd_workspace": (_i64, [_vp, _i32, _i32, _i32]),
     "tecgat_edge_bwd": (C.c_int, [_vp] * 13 + [_i32, _i32, _i32, _f32, _f32, _u64, _i32, _i32, _vp]),
     "tecgat_forward": (C.c_int, [_vp] * 12 + [_i32, _i32, _i32, _i32, _f32, _f32, _u64, _vp, _i32, _i32, _i32, _vp]),
+    "tecgat_forward_into": (C.c_int, [_vp] * 12 + [_i32, _i32, _i32, _i32, _f32, _f32, _u64, _vp, _i32, _i32, _i32, _vp, _i64, _vp]),
     "tecgat_backward_workspace": (_i64, [_vp, _i32, _i32, _i32, _i32, _i32]),
     "tecgat_backward_fused_supported": (C.c_int, [_i32, _i32, _i32]),
     "tecgat_backward": (C.c_int, [_vp] * 14 + [_i32] + [_vp] * 6 + [_i32, _vp, _i32, _i32, _i32, _i32, _f32, _f32, _u64, _vp,

@@ -279,7 +279,8 @@ struct DropCfg {
 // internal entry points behind the C ABI (seed_dev != NULL: the dropout seed is read from device memory)
 int edge_fwd_run(const tecgat_plan_t *plan, const void *xl, const void *xr, const float *att, const float *bias, float *y,
                  float *stat, int32_t snapshots, int32_t heads, int32_t out_channels, float negative_slope, float dropout_p,
-                 uint64_t seed, const uint64_t *seed_dev, int32_t mode, int32_t dtype, void *stream);
+                 uint64_t seed, const uint64_t *seed_dev, int32_t mode, int32_t dtype, void *stream, float *y_wide = nullptr,
+                 int64_t ld_wide = 0);
 // reduce = false: leave the per-CTA partial rows of d att / d bias in `workspace` (*partial_rows of them, width 2*H*C)
 // for the caller's own second stage
 int edge_bwd_run(const tecgat_plan_t *plan, const void *xl, const void *xr, const float *att, const float *bias, const float *y,

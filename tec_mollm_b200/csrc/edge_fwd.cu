@@ -27,6 +27,8 @@ struct EdgeFwdArgs {
     const int32_t *rowptr, *col;  // destination-sorted CSR (tiles that are not staged)
     int32_t N, T, num_tiles, S, H, npw;
     float slope, inv_keep;
+    float *y2;     // optional second copy of the output rows inside a wider row-major tensor (row stride ld2 floats), or NULL
+    int64_t ld2;
     uint32_t drop_thr;
     uint32_t stream_stride;  // dropout counter distance between consecutive (snapshot, head) streams
     uint64_t seed;
@@ -259,6 +261,21 @@ __global__ void __launch_bounds__(512, 1) edge_fwd_kernel(const EdgeFwdArgs a) {
             } else {
                 for (int i = lane; i < nv * HC; i += 32) y_g[i] = ybuf[i];
             }
+            if (a.y2) {  // the same rows into the caller's wider tensor (one HC-float run per row)
+                float *y_w = a.y2 + ((int64_t)snap * N + n0 + warp * npw) * a.ld2;
+                if (VEC) {
+                    const int hw = HC / 2;
+                    for (int i = lane; i < nv * hw; i += 32) {
+                        const int r = i / hw, c = i - r * hw;
+                        reinterpret_cast<float2 *>(y_w + (int64_t)r * a.ld2)[c] = reinterpret_cast<const float2 *>(ybuf)[i];
+                    }
+                } else {
+                    for (int i = lane; i < nv * HC; i += 32) {
+                        const int r = i / HC, c = i - r * HC;
+                        y_w[(int64_t)r * a.ld2 + c] = ybuf[i];
+                    }
+                }
+            }
             __syncwarp();
         } else if constexpr (GATHER) {
             // window or degree too large for a stage: gather straight from global memory (L2)
@@ -274,6 +291,7 @@ __global__ void __launch_bounds__(512, 1) edge_fwd_kernel(const EdgeFwdArgs a) {
             fwd_lane<C, ST, VEC, false, DROP>(Ts, a, attp, attm, bias_h, xr_chunk, xl_snap + (int64_t)(n0 + node_l) * HC, xl_snap, HC, par, nullptr,
                                         a.col + k0, deg, kmax_w, (uint32_t)k0, key, out, stat);
             if (active) cv_store<C, VEC>(a.y + row * HC + hh * C, out, par);
+            if (active && a.y2) cv_store<C, VEC>(a.y2 + row * a.ld2 + hh * C, out, par);
         }
         if (active) a.stat[row * H + hh] = stat;
         if (++tile == a.num_tiles) { tile = 0; ++snap; }
@@ -420,8 +438,11 @@ extern "C" int tecgat_edge_fwd(const tecgat_plan_t *plan, const void *xl, const 
 
 int tg::edge_fwd_run(const tecgat_plan_t *plan, const void *xl, const void *xr, const float *att, const float *bias, float *y,
                      float *stat, int32_t snapshots, int32_t heads, int32_t out_channels, float negative_slope, float dropout_p,
-                     uint64_t seed, const uint64_t *seed_dev, int32_t mode, int32_t dtype, void *stream) {
+                     uint64_t seed, const uint64_t *seed_dev, int32_t mode, int32_t dtype, void *stream, float *y_wide,
+                     int64_t ld_wide) {
     using namespace tg;
+    TG_REQUIRE(!y_wide || (reinterpret_cast<uintptr_t>(y_wide) % 8 == 0 && ld_wide % 2 == 0 && ld_wide >= int64_t(heads) * out_channels),
+               TECGAT_EINVAL, "edge_fwd: the wide output must be 8-byte aligned with an even row stride >= heads * out_channels");
     TG_REQUIRE(plan && xl && xr && att && bias && y && stat, TECGAT_EINVAL, "edge_fwd: NULL argument");
     TG_REQUIRE(snapshots > 0 && heads > 0 && out_channels > 0, TECGAT_EINVAL, "edge_fwd: non-positive size");
     TG_REQUIRE(heads <= 32, TECGAT_ENOSUP, "edge_fwd: heads %d > 32", heads);
@@ -440,6 +461,7 @@ int tg::edge_fwd_run(const tecgat_plan_t *plan, const void *xl, const void *xr, 
                TECGAT_EINVAL, "edge_fwd: xl / xr / y must be 16-byte aligned");
     EdgeFwdArgs a;
     a.xl = xl; a.xr = xr; a.att = att; a.bias = bias; a.y = y; a.stat = stat;
+    a.y2 = y_wide; a.ld2 = ld_wide;
     a.meta = tl.meta; a.slabs = tl.slabs;
     a.rowptr = plan->rowptr_in; a.col = plan->col_in;
     a.N = plan->num_nodes; a.T = tl.T; a.num_tiles = tl.num_tiles; a.S = snapshots; a.H = heads; a.npw = 0;

@@ -89,6 +89,15 @@ extern "C" int tecgat_forward(const tecgat_plan_t *plan, const float *x, const f
                               int32_t snapshots, int32_t in_channels, int32_t heads, int32_t out_channels, float negative_slope,
                               float dropout_p, uint64_t seed, const uint64_t *seed_dev, int32_t mode, int32_t dtype, int32_t impl,
                               void *stream) {
+    return tecgat_forward_into(plan, x, wl, bl, wr, br, att, bias, xl, xr, y, stat, snapshots, in_channels, heads, out_channels,
+                               negative_slope, dropout_p, seed, seed_dev, mode, dtype, impl, nullptr, 0, stream);
+}
+
+extern "C" int tecgat_forward_into(const tecgat_plan_t *plan, const float *x, const float *wl, const float *bl, const float *wr,
+                                   const float *br, const float *att, const float *bias, void *xl, void *xr, float *y, float *stat,
+                                   int32_t snapshots, int32_t in_channels, int32_t heads, int32_t out_channels,
+                                   float negative_slope, float dropout_p, uint64_t seed, const uint64_t *seed_dev, int32_t mode,
+                                   int32_t dtype, int32_t impl, float *y_wide, int64_t ld_wide, void *stream) {
     TG_REQUIRE(plan, TECGAT_EINVAL, "forward: NULL plan");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int64_t rows = int64_t(snapshots) * plan->num_nodes;
@@ -97,7 +106,7 @@ extern "C" int tecgat_forward(const tecgat_plan_t *plan, const float *x, const f
     if (rc != TECGAT_OK) return rc;
     tg::phase_mark(0, st);
     rc = tg::edge_fwd_run(plan, xl, xr, att, bias, y, stat, snapshots, heads, out_channels, negative_slope, dropout_p, seed, seed_dev,
-                          mode, dtype, stream);
+                          mode, dtype, stream, y_wide, ld_wide);
     tg::phase_mark(1, st);
     return rc;
 }

@@ -225,6 +225,91 @@ class _GATv2Function(torch.autograd.Function):
         return (dx, dwl, dbl, dwr, dbr, datt, dbias) + (None,) * 13
 
 
+class _GATv2PairsFunction(torch.autograd.Function):
+    """``H`` heads as ``H / 2`` independent two-head layers on parameter slices (``GATv2Conv._split_head_pairs``) in ONE autograd
+    node: every pair's edge kernel also writes its columns of the ``(rows, H*C)`` output (``tecgat_forward_into``: no concat
+    pass), the backward accumulates ``dx`` across the pairs inside the projection's epilogue and writes each pair's parameter
+    gradients straight into its slice of the full-size gradient tensors."""
+
+    @staticmethod
+    def forward(ctx, x2d, wl, bl, wr, br, att, bias, plan: GraphPlan, S, H, Cc, slope, p, seed_ts, mode, dtype, impl):
+        dev = x2d.device
+        R, F = x2d.shape
+        HC, C2 = H * Cc, 2 * Cc
+        st_dtype = torch.float32 if dtype == _lib.F32 else torch.bfloat16
+        out = torch.empty((R, HC), device=dev, dtype=torch.float32)
+        saved = []
+        with _on_device(dev):
+            stream = _stream(dev)
+            for g in range(H // 2):
+                xl = torch.empty((R, C2), device=dev, dtype=st_dtype)
+                xr = torch.empty((R, C2), device=dev, dtype=st_dtype)
+                y = torch.empty((R, C2), device=dev, dtype=torch.float32)   # dense copy: the backward's bulk-TMA source
+                stat = torch.empty((R, 2), device=dev, dtype=torch.float32)
+                o = g * C2
+                _lib.call("tecgat_forward_into", plan.handle, _ptr(x2d), C.c_void_p(wl.data_ptr() + 4 * o * F), C.c_void_p(bl.data_ptr() + 4 * o),
+                          C.c_void_p(wr.data_ptr() + 4 * o * F), C.c_void_p(br.data_ptr() + 4 * o), C.c_void_p(att.data_ptr() + 4 * o),
+                          C.c_void_p(bias.data_ptr() + 4 * o), _ptr(xl), _ptr(xr), _ptr(y), _ptr(stat), S, F, 2, Cc, slope, p, 0,
+                          _ptr(seed_ts[g]) if seed_ts else None, mode, dtype, impl, C.c_void_p(out.data_ptr() + 4 * o), HC, stream)
+                saved += [xl, xr, y, stat]
+        ctx.save_for_backward(x2d, wl, wr, att, bias, *saved)
+        ctx.plan = plan
+        ctx.cfg = (S, H, Cc, slope, p, mode, dtype, impl)
+        ctx.seed_ts = seed_ts
+        return out
+
+    @staticmethod
+    def backward(ctx, gy):
+        x2d, wl, wr, att, bias, *saved = ctx.saved_tensors
+        S, H, Cc, slope, p, mode, dtype, impl = ctx.cfg
+        plan: GraphPlan = ctx.plan
+        dev = x2d.device
+        R, F = x2d.shape
+        HC, C2 = H * Cc, 2 * Cc
+        if gy.dtype != torch.float32:
+            gy = gy.float()
+        L = _lib.lib()
+        need_dx = ctx.needs_input_grad[0]
+        fused_ok = L.tecgat_backward_fused_supported(F, C2, impl) == 1 and x2d.data_ptr() % 16 == 0
+        dwl = torch.empty((HC, F), device=dev, dtype=torch.float32)
+        dwr = torch.empty((HC, F), device=dev, dtype=torch.float32)
+        dbl = torch.empty((HC,), device=dev, dtype=torch.float32)
+        dbr = torch.empty((HC,), device=dev, dtype=torch.float32)
+        datt = torch.empty((1, H, Cc), device=dev, dtype=torch.float32)
+        dbias = torch.empty((HC,), device=dev, dtype=torch.float32)
+        dx = torch.empty_like(x2d) if need_dx else None
+        with _on_device(dev):  # autograd worker threads do not always inherit the current device
+            stream = _stream(dev)
+            ws = torch.empty((max(1, L.tecgat_backward_workspace(plan.handle, S, F, 2, Cc, impl)),), device=dev, dtype=torch.uint8)
+            for g in range(H // 2):
+                xl, xr, y, stat = saved[4 * g:4 * g + 4]
+                o = g * C2
+                g_g = gy[:, o:o + C2].contiguous()   # the edge kernel stages windows of dense rows
+                dxl = torch.empty_like(xl)
+                dxr = torch.empty_like(xr)
+                # dx: pair 0 writes, later pairs accumulate in the projection's epilogue (or through a temporary + add)
+                acc = int(need_dx and g > 0 and fused_ok)
+                dx_g = dx if (g == 0 or acc or not need_dx) else torch.empty_like(x2d)
+                if fused_ok:  # the gradient finish writes plain floats: straight into the slices
+                    tg = [C.c_void_p(dwl.data_ptr() + 4 * o * F), C.c_void_p(dbl.data_ptr() + 4 * o), C.c_void_p(dwr.data_ptr() + 4 * o * F),
+                          C.c_void_p(dbr.data_ptr() + 4 * o), C.c_void_p(datt.data_ptr() + 4 * o), C.c_void_p(dbias.data_ptr() + 4 * o)]
+                    tmp = None
+                else:
+                    tmp = [torch.empty((C2, F), device=dev), torch.empty((C2,), device=dev), torch.empty((C2, F), device=dev),
+                           torch.empty((C2,), device=dev), torch.empty((C2,), device=dev), torch.empty((C2,), device=dev)]
+                    tg = [_ptr(t) for t in tmp]
+                _lib.call("tecgat_backward", plan.handle, _ptr(x2d), C.c_void_p(wl.data_ptr() + 4 * o * F), C.c_void_p(wr.data_ptr() + 4 * o * F),
+                          C.c_void_p(att.data_ptr() + 4 * o), C.c_void_p(bias.data_ptr() + 4 * o), _ptr(xl), _ptr(xr), _ptr(y), _ptr(stat),
+                          _ptr(g_g), _ptr(dxl), _ptr(dxr), _ptr(dx_g), acc, tg[0], tg[1], tg[2], tg[3], tg[4], tg[5], 0, _ptr(ws),
+                          S, F, 2, Cc, slope, p, 0, _ptr(ctx.seed_ts[g]) if ctx.seed_ts else None, mode, dtype, impl, stream)
+                if tmp is not None:
+                    dwl[o:o + C2].copy_(tmp[0]); dbl[o:o + C2].copy_(tmp[1]); dwr[o:o + C2].copy_(tmp[2]); dbr[o:o + C2].copy_(tmp[3])
+                    datt.view(-1)[o:o + C2].copy_(tmp[4]); dbias[o:o + C2].copy_(tmp[5])
+                if need_dx and dx_g is not dx:
+                    dx += dx_g
+        return (dx, dwl, dbl, dwr, dbr, datt, dbias) + (None,) * 10
+
+
 class _Linear(nn.Module):
     """Parameter holder with ``torch_geometric.nn.dense.Linear``'s names (``weight``, ``bias``) and
     init (glorot weight, U(+-1/sqrt(in)) bias)."""
@@ -388,24 +473,19 @@ class GATv2Conv(nn.Module):
         return self.heads > 2 and self.heads % 2 == 0 and self.out_channels in (5, 11)
 
     def _forward_head_pairs(self, x, edge_index, snapshots, num_nodes, p, mode, dtype):
-        C2 = 2 * self.out_channels
         plan = self.plan_for(edge_index, num_nodes, (tile_nodes_for(2), tile_nodes_for(2, backward=True, out_channels=self.out_channels)))
-        f32 = lambda t: t if t.dtype == torch.float32 else t.float()
-        wl, bl, wr, br = f32(self.lin_l.weight), f32(self.lin_l.bias), f32(self.lin_r.weight), f32(self.lin_r.bias)
-        att, bias = f32(self.att), f32(self.bias)
-        ys = []
-        for g in range(self.heads // 2):
-            sl = slice(g * C2, (g + 1) * C2)
-            seed_t = None
-            if p > 0.0:  # every pair draws its own seed: the kernels number the (snapshot, head) streams inside one call
-                seed_t = torch.empty(1, dtype=torch.int64, device=x.device)
-                with _on_device(x.device):
+        f32c = lambda t: (t if t.dtype == torch.float32 else t.float()).contiguous()
+        seed_ts = None
+        if p > 0.0:  # every pair draws its own seed: the kernels number the (snapshot, head) streams inside one call
+            seed_ts = []
+            with _on_device(x.device):
+                for _ in range(self.heads // 2):
+                    seed_t = torch.empty(1, dtype=torch.int64, device=x.device)
                     _lib.call("tecgat_seed_advance", _ptr(self._dropout_state(x.device)), _ptr(seed_t), _stream(x.device))
-            al = lambda t: t if t.data_ptr() % 16 == 0 else t.clone()  # parameter slices start 88 bytes into their tensors
-            ys.append(_GATv2Function.apply(x, al(wl[sl]), al(bl[sl]), al(wr[sl]), al(br[sl]), al(att[:, 2 * g:2 * g + 2]), al(bias[sl]),
-                                           plan, snapshots, 2, self.out_channels, self.negative_slope, p, 0, seed_t, mode, dtype,
-                                           _proj_impl(), None, None))
-        return torch.cat(ys, dim=1)
+                    seed_ts.append(seed_t)
+        return _GATv2PairsFunction.apply(x, f32c(self.lin_l.weight), f32c(self.lin_l.bias), f32c(self.lin_r.weight), f32c(self.lin_r.bias),
+                                         f32c(self.att), f32c(self.bias), plan, snapshots, self.heads, self.out_channels,
+                                         self.negative_slope, p, seed_ts, mode, dtype, _proj_impl())
 
     def forward(self, x: torch.Tensor, edge_index: torch.Tensor, edge_attr=None, return_attention_weights=None):
         """PyG semantics for one 2-D input: ``num_nodes = x.size(0)`` rows, edges as given (so calling it the way

@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol(lib):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/tecgat.h but not exported"
     assert sorted(_lib.EXPORTED_SYMBOLS) == names, "ctypes signature table and header disagree"
-    assert lib.tecgat_abi_version() == _lib.ABI_VERSION == 3
+    assert lib.tecgat_abi_version() == _lib.ABI_VERSION == 4
 
 
 def test_library_is_sm100a_native(lib):
