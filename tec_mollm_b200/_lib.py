@@ -11,7 +11,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libtecgat.so")
+LIB_PATH = os.environ.get("TECGAT_LIB") or os.path.join(_HERE, "lib", "libtecgat.so")  # TECGAT_LIB: A/B builds (tools/tune_edge_bwd.py)
 
 F32, BF16 = 0, 1
 MODE_SHARED, MODE_LITERAL = 0, 1

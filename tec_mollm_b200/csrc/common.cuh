@@ -47,6 +47,9 @@ int tg_sm_count();
 cudaError_t tg_set_smem(const void *kernel, int bytes);
 // environment tuning knobs, read once per process (getenv on every launch shows up at B = 2)
 const char *tg_env(const char *name);
+// item schedule (plan.cu): (grid + 1) host array, valid for the plan's lifetime
+struct tecgat_plan;
+const int64_t *tg_item_bounds(const struct tecgat_plan *plan, bool bwd, int64_t snapshots, int grid, int64_t *max_items);
 
 // One tiling of the node axis: tiles of T consecutive nodes, each with the contiguous row window [lo, hi) it touches and
 // a "slab" -- the tile's slice of the graph in ELL form, laid out so that ONE bulk-TMA copy brings it into shared memory:
@@ -74,6 +77,9 @@ struct tg_tiling {
     unsigned char *slabs = nullptr;  // device
     std::vector<tg_tile_meta> h_meta;
     std::vector<int64_t> h_slab_off;  // (tiles + 1)
+    // Item schedule: the persistent CTAs take contiguous item ranges of equal estimated WORK, not equal count (a polar tile of
+    // the 64,800-node grid costs 50 x an equatorial one).  h_cost_prefix[t] = sum of the cost estimates of tiles < t.
+    std::vector<int64_t> h_cost_prefix;  // (tiles + 1)
 };
 
 // Sliding-window backward tiling (edge_bwd_sw.cu): chunks of T consecutive nodes whose in- and out-neighbours all lie within
@@ -116,6 +122,14 @@ struct tecgat_plan {
     // (kernel, heads, channels, dtype) from the tilings instead of on every launch; POD blobs keyed by the launcher
     mutable std::mutex cache_mu;
     mutable std::map<uint64_t, std::vector<unsigned char>> geom_cache;
+    // item schedule of the persistent edge kernels per (direction, snapshots, grid): bounds[b] .. bounds[b + 1] = the items of
+    // CTA b, contiguous ranges of equal estimated work (tg_tiling::h_cost_prefix); computed once, handed to the kernels as a
+    // kernel-parameter array (constant bank: the CTA's range stays in uniform registers, which a global load would not)
+    struct ItemBounds {
+        std::vector<int64_t> host;  // (grid + 1)
+        int64_t max_items = 0;      // largest range
+    };
+    mutable std::map<uint64_t, ItemBounds> bounds_cache;
     // sliding-window backward tiling (edge_bwd_sw.cu), built by plan_create when the graph is banded
     struct tg_sw_plan *sw = nullptr;
 };

@@ -46,6 +46,7 @@ struct EdgeBwdArgs {
     uint32_t stage_bytes, off_meta, off_red, off_stage0, off_y, off_out, off_statraw, off_ds, off_xl, off_xr, off_g;
     int32_t max_flushes;  // partial rows per CTA
     int64_t items;
+    ItemSchedule sched;  // which items each CTA takes (equal estimated work)
 };
 
 // score of an out-edge (v -> u) from the source's side:  c1 + att_m . |xl_v + xr_u|   (c1 = att_p . xl_v)
@@ -111,11 +112,20 @@ __device__ __forceinline__ void bwd_lane(const CV<C> &attp, const CV<C> &attm, c
     for (int k = 1; k < kmax_in; k += 2, hk += 2u * kDropMul) {
         const ptrdiff_t na = nbr_in(k + 2), nb = nbr_in(k + 3);
         CV<C> xa, xb, sa, sb;
+#if TG_TUNE & 1
+        asm volatile("" ::: "memory");
+#endif
         cv_load<C, VEC>(xa, xl_base + ua * HC, par);
         cv_load<C, VEC>(xb, xl_base + ub * HC, par);
+#if TG_TUNE & 4
+        const float ga = cv_dot<C>(g_v, xa), gb = cv_dot<C>(g_v, xb);
+        const float ea = edge_score<C>(attp, attm, xa, xr_v, sa);
+        const float eb = edge_score<C>(attp, attm, xb, xr_v, sb);
+#else
         const float ea = edge_score<C>(attp, attm, xa, xr_v, sa);
         const float eb = edge_score<C>(attp, attm, xb, xr_v, sb);
         const float ga = cv_dot<C>(g_v, xa), gb = cv_dot<C>(g_v, xb);
+#endif
         const float va = k < deg_in ? 1.f : 0.f, vb = k + 1 < deg_in ? 1.f : 0.f;
         const float aa = va * fast_exp2(fminf(ea - dv.y, 100.f)), ab = vb * fast_exp2(fminf(eb - dv.y, 100.f));
         const float da = aa * fmaf(drop.qh(hk), ga, -dv.x);
@@ -127,8 +137,13 @@ __device__ __forceinline__ void bwd_lane(const CV<C> &attp, const CV<C> &attm, c
         ub = nb;
     }
     // ---- role 2: v as SOURCE, out-edges (v -> u): A_out, B_out, G = sum alpha q g_u ------------------------------
+#if TG_TUNE & 32
+    const float c1 = cv_dot<C>(attp, xl_v);
+    wait_ds();  // the (delta, stat) of every window row has been written (other warps' pre-pass shares)
+#else
     wait_ds();  // the (delta, stat) of every window row has been written (other warps' pre-pass shares)
     const float c1 = cv_dot<C>(attp, xl_v);
+#endif
     ua = nbr_out(1);
     ub = nbr_out(2);
     uint32_t sla = slot_out(1), slb = slot_out(2);
@@ -137,6 +152,9 @@ __device__ __forceinline__ void bwd_lane(const CV<C> &attp, const CV<C> &attm, c
         const ptrdiff_t na = nbr_out(k + 2), nb = nbr_out(k + 3);
         const uint32_t nsa = slot_out(k + 2), nsb = slot_out(k + 3);
         CV<C> ra, rb, ga, gb, sa, sb;
+#if TG_TUNE & 2
+        asm volatile("" ::: "memory");
+#endif
         cv_load<C, VEC>(ra, xr_base + ua * HC, par);
         cv_load<C, VEC>(rb, xr_base + ub * HC, par);
         cv_load<C, VEC>(ga, g_base + ua * HC, par);
@@ -150,10 +168,17 @@ __device__ __forceinline__ void bwd_lane(const CV<C> &attp, const CV<C> &attm, c
         const float qa = drop.q(sla), qb = drop.q(slb);
         const float da = aa * fmaf(qa, gxa, -dua.x), db = ab * fmaf(qb, gxb, -dub.x);
         A_out += da + db;
+#if TG_TUNE & 64
+        cv_axpy<C>(G, aa * qa, ga);
+        cv_axpy<C>(G, ab * qb, gb);
+        acc_step<C>(B_out, sa, da);
+        acc_step<C>(B_out, sb, db);
+#else
         acc_step<C>(B_out, sa, da);
         acc_step<C>(B_out, sb, db);
         cv_axpy<C>(G, aa * qa, ga);
         cv_axpy<C>(G, ab * qb, gb);
+#endif
         ua = na; ub = nb;
         sla = nsa; slb = nsb;
     }
@@ -181,9 +206,21 @@ __device__ __forceinline__ void bwd_lane(const CV<C> &attp, const CV<C> &attm, c
 // WG: 384-thread CTA = 8 consumer warps (two warpgroups) + one producer warpgroup; the producer group hands its registers to
 // the consumers (setmaxnreg), which lifts the consumers to 8 warps x 240 registers -- the register file's split per scheduler
 // (16 K registers each) would otherwise cap a 9-warp CTA at 168 registers per thread.
+// TG_TUNE: bit switches over semantically neutral variations of this file (statement order, compiler scheduling fences, register
+// split).  ptxas' instruction schedule of the two edge loops moves by +-4 % with ANY change to the kernel, so the default below is
+// the measured best of tools/tune_edge_bwd.py (profiles/r02_edge_bwd_tune.md); re-run it after touching this file.
+#ifndef TG_TUNE
+#define TG_TUNE 0
+#endif
+#if TG_TUNE & 8
+constexpr int kWgConsumerRegs = 224, kWgProducerRegs = 40;
+#elif TG_TUNE & 16
+constexpr int kWgConsumerRegs = 240, kWgProducerRegs = 24;
+#else
 constexpr int kWgConsumerRegs = 232, kWgProducerRegs = 40;
+#endif
 template <int C, typename ST, bool VEC, int HT, bool SEMI, bool GATHER, bool DROP, bool WG = false>
-__global__ void __launch_bounds__(WG ? 384 : 256, 1) edge_bwd_kernel(const EdgeBwdArgs a) {
+__global__ void __launch_bounds__(WG ? 384 : 256, 1) edge_bwd_kernel(const __grid_constant__ EdgeBwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem);
     uint64_t *empty = full + kMaxStages;
@@ -215,7 +252,7 @@ __global__ void __launch_bounds__(WG ? 384 : 256, 1) edge_bwd_kernel(const EdgeB
         for (int i = threadIdx.x; i < a.num_tiles * 8; i += blockDim.x)
             reinterpret_cast<int32_t *>(smem + a.off_meta)[i] = reinterpret_cast<const int32_t *>(a.meta)[i];
     __syncthreads();
-    const ItemRange R = cta_items(a.items);
+    const ItemRange R = cta_items_scheduled(a.sched, a.items);
     int snap = (int)(R.w0 / a.num_tiles), tile = (int)(R.w0 % a.num_tiles);
     const int n_items = (int)(R.w1 - R.w0);  // 32-bit loop counter (a CTA never owns 2^31 items)
     const int64_t Rtot = (int64_t)a.S * N;
@@ -619,9 +656,12 @@ static int bwd_grid(const tecgat_plan_t *plan, int32_t snapshots) {
 }
 
 static int bwd_max_flushes(const tecgat_plan_t *plan, int32_t snapshots) {  // partial rows per CTA
-    const int64_t items = int64_t(plan->bwd.num_tiles) * snapshots;
     const int g = bwd_grid(plan, snapshots);
-    return (int)(((items + g - 1) / g) / kFlushItems + 1);
+    int64_t max_items = 0;
+    tg_item_bounds(plan, true, snapshots, g, &max_items);
+    const int64_t items = int64_t(plan->bwd.num_tiles) * snapshots;
+    max_items = std::max(max_items, (items + g - 1) / g);  // the equal-count fallback
+    return (int)(max_items / kFlushItems + 1);
 }
 
 struct BwdGeomCached {  // everything launch_bwd derives from (tiling, heads, channels, dtype): cached in the plan
@@ -711,6 +751,7 @@ static int launch_bwd(EdgeBwdArgs a, const tecgat_plan_t *plan, int grid, cudaSt
     const bool wg = ncw == 8;  // 8 consumer warps: only as the warpgroup-split kernels (specialised shapes)
     auto go = [&](auto kern) -> int {
         TG_CUDA(tg_set_smem(reinterpret_cast<const void *>(kern), (int)smem));
+        fill_schedule(a.sched, plan, true, a.S, grid);
         kern<<<(unsigned)grid, wg ? 384 : (ncw + 1) * 32, smem, st>>>(a);
         tg_count_launch();
         return TECGAT_OK;
@@ -719,18 +760,27 @@ static int launch_bwd(EdgeBwdArgs a, const tecgat_plan_t *plan, int grid, cudaSt
     if (wg) {
         rc = TECGAT_ENOSUP;
         if constexpr (HT > 0) {
+#ifdef TG_TUNE_DEFAULT_ONLY
+            if (!a.semi && all_staged && a.drop_thr != 0) rc = go(edge_bwd_kernel<C, ST, VEC, HT, false, false, true, true>);
+#else
             if (a.semi) rc = go(edge_bwd_kernel<C, ST, VEC, HT, true, true, true, true>);
             else if (all_staged && a.drop_thr == 0) rc = go(edge_bwd_kernel<C, ST, VEC, HT, false, false, false, true>);
             else if (all_staged) rc = go(edge_bwd_kernel<C, ST, VEC, HT, false, false, true, true>);
             else rc = go(edge_bwd_kernel<C, ST, VEC, HT, false, true, true, true>);
+#endif
         }
         if (rc == TECGAT_ENOSUP)
             tecgat_set_error("edge_bwd: a backward tile of %d nodes x %d heads (8 consumer warps) exists only for the specialised shapes "
                              "(heads = 2, out_channels 5 or 11); build the plan with tile_nodes_bwd = %d", T, H, 7 * a.npw);
-    } else if (a.semi) rc = go(edge_bwd_kernel<C, ST, VEC, HT, true, true, true>);
+    }
+#ifndef TG_TUNE_DEFAULT_ONLY
+    else if (a.semi) rc = go(edge_bwd_kernel<C, ST, VEC, HT, true, true, true>);
     else if (HT > 0 && all_staged && a.drop_thr == 0) rc = go(edge_bwd_kernel<C, ST, VEC, HT, false, HT == 0, HT == 0>);  // inference: no hash either
     else if (HT > 0 && all_staged) rc = go(edge_bwd_kernel<C, ST, VEC, HT, false, HT == 0, true>);  // compact: no gather code
     else rc = go(edge_bwd_kernel<C, ST, VEC, HT, false, true, true>);
+#else
+    else rc = TECGAT_ENOSUP;
+#endif
     if (rc != TECGAT_OK) return rc;
     TG_LAUNCH_CHECK();
     return TECGAT_OK;
@@ -816,6 +866,10 @@ int tg::edge_bwd_run(const tecgat_plan_t *plan, const void *xl, const void *xr, 
         if (vec) rc = dtype == TECGAT_F32 ? launch_bwd<CC, float, true>(a, plan, grid, st) : launch_bwd<CC, __nv_bfloat16, true>(a, plan, grid, st); \
         else if constexpr ((CC % 2) == 1) rc = dtype == TECGAT_F32 ? launch_bwd<CC, float, false>(a, plan, grid, st) : launch_bwd<CC, __nv_bfloat16, false>(a, plan, grid, st); \
         break;
+#ifdef TG_TUNE_DEFAULT_ONLY  // tools/tune_edge_bwd.py: compile the default workload's kernel alone (seconds instead of minutes)
+    if (heads == 2 && vec && out_channels == 11 && dtype == TECGAT_F32) rc = launch_bwd<11, float, true, 2>(a, plan, grid, st);
+    else return TECGAT_ENOSUP;
+#else
     if (heads == 2 && vec && (out_channels == 11 || out_channels == 5)) {  // compile-time heads for the reference's shapes
         if (out_channels == 11) rc = dtype == TECGAT_F32 ? launch_bwd<11, float, true, 2>(a, plan, grid, st) : launch_bwd<11, __nv_bfloat16, true, 2>(a, plan, grid, st);
         else rc = dtype == TECGAT_F32 ? launch_bwd<5, float, true, 2>(a, plan, grid, st) : launch_bwd<5, __nv_bfloat16, true, 2>(a, plan, grid, st);
@@ -826,6 +880,7 @@ int tg::edge_bwd_run(const tecgat_plan_t *plan, const void *xl, const void *xr, 
             tecgat_set_error("edge_bwd: out_channels=%d is not among the compiled channel counts", out_channels);
             return TECGAT_ENOSUP;
     }
+#endif
 #undef TG_CASE
     if (rc != TECGAT_OK) return rc;
     if (partial_rows) *partial_rows = int64_t(grid) * a.max_flushes;

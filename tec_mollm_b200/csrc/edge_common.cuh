@@ -175,6 +175,31 @@ __device__ __forceinline__ ItemRange cta_items(int64_t items) {
     r.w1 = items * (blockIdx.x + 1) / gridDim.x;
     return r;
 }
+// Contiguous item ranges of equal estimated work: computed on the host (tg_item_bounds, plan.cu) and passed INSIDE the kernel
+// parameters -- read from the constant bank with a uniform index, so the CTA's (snapshot, tile, count) bookkeeping stays in
+// uniform registers exactly as with the closed-form split (loading the two bounds from global memory instead cost 2.5 % of
+// edge_bwd: the loop counters became vector registers).  Grids beyond kMaxSchedGrid use equal item counts.
+constexpr int kMaxSchedGrid = 191;
+struct ItemSchedule {
+    int32_t use;                        // 0: equal item counts (closed form)
+    int32_t pad;
+    int64_t bounds[kMaxSchedGrid + 1];  // CTA b: items [bounds[b], bounds[b + 1])
+};
+__device__ __forceinline__ ItemRange cta_items_scheduled(const ItemSchedule &s, int64_t items) {
+    if (!s.use) return cta_items(items);
+    ItemRange r;
+    r.w0 = s.bounds[blockIdx.x];
+    r.w1 = s.bounds[blockIdx.x + 1];
+    return r;
+}
+inline void fill_schedule(ItemSchedule &s, const tecgat_plan_t *plan, bool bwd, int64_t snapshots, int grid) {
+    s.use = 0;
+    s.pad = 0;
+    if (grid > kMaxSchedGrid) return;
+    const int64_t *b = tg_item_bounds(plan, bwd, snapshots, grid, nullptr);
+    for (int i = 0; i <= grid; ++i) s.bounds[i] = b[i];
+    s.use = 1;
+}
 
 // ring position: stage index and mbarrier phase parity, advanced without divisions
 struct Ring {

@@ -23,6 +23,7 @@ struct EdgeFwdArgs {
     const float *att, *bias;
     float *y, *stat;
     const tg_tile_meta *meta;
+    ItemSchedule sched;  // which items each CTA takes (equal estimated work)
     const unsigned char *slabs;
     const int32_t *rowptr, *col;  // destination-sorted CSR (tiles that are not staged)
     int32_t N, T, num_tiles, S, H, npw;
@@ -133,7 +134,7 @@ __device__ __forceinline__ void fwd_lane(const int Ts /* slab row stride */, con
 // GATHER: the launch contains tiles that are not staged (false drops the gather-from-global code: every item is staged).
 // TT > 0: compile-time tile size (nodes) -- the default 15 consumer warps x 32 / heads: the slab strides become immediates
 template <int C, typename ST, bool VEC, int HT, bool GATHER, bool DROP, int TT = 0>
-__global__ void __launch_bounds__(512, 1) edge_fwd_kernel(const EdgeFwdArgs a) {
+__global__ void __launch_bounds__(512, 1) edge_fwd_kernel(const __grid_constant__ EdgeFwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem);
     uint64_t *empty = full + kMaxStages;
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(512, 1) edge_fwd_kernel(const EdgeFwdArgs a) {
         for (int i = threadIdx.x; i < a.num_tiles * 8; i += blockDim.x)
             reinterpret_cast<int32_t *>(smem + a.off_meta)[i] = reinterpret_cast<const int32_t *>(a.meta)[i];
     __syncthreads();
-    const ItemRange R = cta_items(a.items);
+    const ItemRange R = cta_items_scheduled(a.sched, a.items);
     int snap = (int)(R.w0 / a.num_tiles), tile = (int)(R.w0 % a.num_tiles);
     const int n_items = (int)(R.w1 - R.w0);  // 32-bit loop counter (a CTA never owns 2^31 items)
     const int64_t Rtot = (int64_t)a.S * N;
@@ -410,6 +411,7 @@ static int launch_fwd(EdgeFwdArgs a, const tecgat_plan_t *plan, cudaStream_t st)
         TG_CUDA(tg_set_smem(reinterpret_cast<const void *>(kern), (int)smem));
         // one persistent CTA per SM (512 threads and > 113 KB of shared memory: never two)
         const int64_t grid = std::min<int64_t>(a.items, int64_t(sms));
+        fill_schedule(a.sched, plan, false, a.S, (int)grid);
         kern<<<(unsigned)grid, (ncw + 1) * 32, smem, st>>>(a);
         tg_count_launch();
         return TECGAT_OK;

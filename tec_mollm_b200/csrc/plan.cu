@@ -78,6 +78,34 @@ static int upload(T **dst, const std::vector<T> &src, cudaStream_t st) {
     return TECGAT_OK;
 }
 
+// Item schedule of a persistent edge kernel: CTA b of `grid` takes items [bounds[b], bounds[b + 1]) of the snapshot-major item
+// list, ranges of equal estimated work (one snapshot's work = h_cost_prefix.back()).  TECGAT_SCHEDULE=count (A/B knob): equal
+// item counts.
+const int64_t *tg_item_bounds(const tecgat_plan_t *plan, bool bwd, int64_t S, int grid, int64_t *max_items) {
+    const tg_tiling &tl = bwd ? plan->bwd : plan->fwd;
+    const bool by_count = tg_env("TECGAT_SCHEDULE") != nullptr;
+    const uint64_t key = (uint64_t(bwd) << 60) | (uint64_t(by_count) << 59) | (uint64_t(S) << 20) | uint64_t(grid);
+    std::lock_guard<std::mutex> lk(plan->cache_mu);
+    auto &e = plan->bounds_cache[key];
+    if (e.host.empty()) {
+        const int64_t W = tl.h_cost_prefix.back(), nt = tl.num_tiles;
+        e.host.resize(size_t(grid) + 1);
+        for (int b = 0; b <= grid; ++b) {
+            if (b == grid || W <= 0 || by_count) {
+                e.host[b] = b == grid ? S * nt : S * nt * b / grid;
+                continue;
+            }
+            const int64_t X = S * W, u = X / grid * b + (X % grid) * b / grid;  // floor(S W b / grid)
+            const int64_t snap = u / W, rem = u - snap * W;
+            const int64_t t = std::upper_bound(tl.h_cost_prefix.begin() + 1, tl.h_cost_prefix.end(), rem) - (tl.h_cost_prefix.begin() + 1);
+            e.host[b] = snap * nt + t;
+        }
+        for (int b = 0; b < grid; ++b) e.max_items = std::max(e.max_items, e.host[b + 1] - e.host[b]);
+    }
+    if (max_items) *max_items = e.max_items;
+    return e.host.data();
+}
+
 static void free_tiling(tg_tiling &t) {
     cudaFree(t.meta);
     cudaFree(t.slabs);
@@ -117,6 +145,7 @@ static int build_tiling(tg_tiling &tl, bool bwd, int32_t T, int64_t N, const std
     tl.num_tiles = static_cast<int32_t>((N + T - 1) / T);
     tl.h_meta.resize(tl.num_tiles);
     tl.h_slab_off.assign(tl.num_tiles + 1, 0);
+    tl.h_cost_prefix.assign(tl.num_tiles + 1, 0);
     for (int32_t t = 0; t < tl.num_tiles; ++t) {
         const int64_t n0 = int64_t(t) * T, n1 = std::min<int64_t>(N, n0 + T);
         int32_t l = static_cast<int32_t>(n0), h = static_cast<int32_t>(n1 - 1), kin = 0, kout = 0;
@@ -145,6 +174,12 @@ static int build_tiling(tg_tiling &tl, bool bwd, int32_t T, int64_t N, const std
         m.eligible = ok ? 1 : 0;
         m.kin_kout = ok ? (kin | (kout << 16)) : 0;
         tl.max_window = std::max(tl.max_window, h + 1 - l);
+        {   // cost estimate in warp instructions per item (the lanes of a tile walk to the tile's longest row): per-item part +
+            // per-slot part, from the kernels' SASS; tiles that can never be staged (gathered from L2) count double
+            int64_t c = bwd ? 930 + 84 * int64_t(kin + kout) : 325 + 56 * int64_t(kin);
+            if (!ok || (h + 1 - l) > 2048 || kin > 96) c *= 2;
+            tl.h_cost_prefix[t + 1] = tl.h_cost_prefix[t] + c;
+        }
         const int64_t bytes = ok ? 16 + 8 * int64_t(Ts) + 2 * int64_t(Ts) * (kin + 2 * kout) : 0;
         tl.h_slab_off[t + 1] = tl.h_slab_off[t] + ((bytes + 15) & ~int64_t(15));
         m.slab_off = tl.h_slab_off[t];
