@@ -112,20 +112,11 @@ __device__ __forceinline__ void bwd_lane(const CV<C> &attp, const CV<C> &attm, c
     for (int k = 1; k < kmax_in; k += 2, hk += 2u * kDropMul) {
         const ptrdiff_t na = nbr_in(k + 2), nb = nbr_in(k + 3);
         CV<C> xa, xb, sa, sb;
-#if TG_TUNE & 1
-        asm volatile("" ::: "memory");
-#endif
         cv_load<C, VEC>(xa, xl_base + ua * HC, par);
         cv_load<C, VEC>(xb, xl_base + ub * HC, par);
-#if TG_TUNE & 4
-        const float ga = cv_dot<C>(g_v, xa), gb = cv_dot<C>(g_v, xb);
-        const float ea = edge_score<C>(attp, attm, xa, xr_v, sa);
-        const float eb = edge_score<C>(attp, attm, xb, xr_v, sb);
-#else
         const float ea = edge_score<C>(attp, attm, xa, xr_v, sa);
         const float eb = edge_score<C>(attp, attm, xb, xr_v, sb);
         const float ga = cv_dot<C>(g_v, xa), gb = cv_dot<C>(g_v, xb);
-#endif
         const float va = k < deg_in ? 1.f : 0.f, vb = k + 1 < deg_in ? 1.f : 0.f;
         const float aa = va * fast_exp2(fminf(ea - dv.y, 100.f)), ab = vb * fast_exp2(fminf(eb - dv.y, 100.f));
         const float da = aa * fmaf(drop.qh(hk), ga, -dv.x);
@@ -137,13 +128,8 @@ __device__ __forceinline__ void bwd_lane(const CV<C> &attp, const CV<C> &attm, c
         ub = nb;
     }
     // ---- role 2: v as SOURCE, out-edges (v -> u): A_out, B_out, G = sum alpha q g_u ------------------------------
-#if TG_TUNE & 32
-    const float c1 = cv_dot<C>(attp, xl_v);
-    wait_ds();  // the (delta, stat) of every window row has been written (other warps' pre-pass shares)
-#else
     wait_ds();  // the (delta, stat) of every window row has been written (other warps' pre-pass shares)
     const float c1 = cv_dot<C>(attp, xl_v);
-#endif
     ua = nbr_out(1);
     ub = nbr_out(2);
     uint32_t sla = slot_out(1), slb = slot_out(2);
@@ -152,9 +138,6 @@ __device__ __forceinline__ void bwd_lane(const CV<C> &attp, const CV<C> &attm, c
         const ptrdiff_t na = nbr_out(k + 2), nb = nbr_out(k + 3);
         const uint32_t nsa = slot_out(k + 2), nsb = slot_out(k + 3);
         CV<C> ra, rb, ga, gb, sa, sb;
-#if TG_TUNE & 2
-        asm volatile("" ::: "memory");
-#endif
         cv_load<C, VEC>(ra, xr_base + ua * HC, par);
         cv_load<C, VEC>(rb, xr_base + ub * HC, par);
         cv_load<C, VEC>(ga, g_base + ua * HC, par);
@@ -168,17 +151,10 @@ __device__ __forceinline__ void bwd_lane(const CV<C> &attp, const CV<C> &attm, c
         const float qa = drop.q(sla), qb = drop.q(slb);
         const float da = aa * fmaf(qa, gxa, -dua.x), db = ab * fmaf(qb, gxb, -dub.x);
         A_out += da + db;
-#if TG_TUNE & 64
-        cv_axpy<C>(G, aa * qa, ga);
-        cv_axpy<C>(G, ab * qb, gb);
-        acc_step<C>(B_out, sa, da);
-        acc_step<C>(B_out, sb, db);
-#else
         acc_step<C>(B_out, sa, da);
         acc_step<C>(B_out, sb, db);
         cv_axpy<C>(G, aa * qa, ga);
         cv_axpy<C>(G, ab * qb, gb);
-#endif
         ua = na; ub = nb;
         sla = nsa; slb = nsb;
     }
@@ -206,19 +182,7 @@ __device__ __forceinline__ void bwd_lane(const CV<C> &attp, const CV<C> &attm, c
 // WG: 384-thread CTA = 8 consumer warps (two warpgroups) + one producer warpgroup; the producer group hands its registers to
 // the consumers (setmaxnreg), which lifts the consumers to 8 warps x 240 registers -- the register file's split per scheduler
 // (16 K registers each) would otherwise cap a 9-warp CTA at 168 registers per thread.
-// TG_TUNE: bit switches over semantically neutral variations of this file (statement order, compiler scheduling fences, register
-// split).  ptxas' instruction schedule of the two edge loops moves by +-4 % with ANY change to the kernel, so the default below is
-// the measured best of tools/tune_edge_bwd.py (profiles/r02_edge_bwd_tune.md); re-run it after touching this file.
-#ifndef TG_TUNE
-#define TG_TUNE 0
-#endif
-#if TG_TUNE & 8
-constexpr int kWgConsumerRegs = 224, kWgProducerRegs = 40;
-#elif TG_TUNE & 16
-constexpr int kWgConsumerRegs = 240, kWgProducerRegs = 24;
-#else
 constexpr int kWgConsumerRegs = 232, kWgProducerRegs = 40;
-#endif
 template <int C, typename ST, bool VEC, int HT, bool SEMI, bool GATHER, bool DROP, bool WG = false>
 __global__ void __launch_bounds__(WG ? 384 : 256, 1) edge_bwd_kernel(const __grid_constant__ EdgeBwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -866,7 +830,7 @@ int tg::edge_bwd_run(const tecgat_plan_t *plan, const void *xl, const void *xr, 
         if (vec) rc = dtype == TECGAT_F32 ? launch_bwd<CC, float, true>(a, plan, grid, st) : launch_bwd<CC, __nv_bfloat16, true>(a, plan, grid, st); \
         else if constexpr ((CC % 2) == 1) rc = dtype == TECGAT_F32 ? launch_bwd<CC, float, false>(a, plan, grid, st) : launch_bwd<CC, __nv_bfloat16, false>(a, plan, grid, st); \
         break;
-#ifdef TG_TUNE_DEFAULT_ONLY  // tools/tune_edge_bwd.py: compile the default workload's kernel alone (seconds instead of minutes)
+#ifdef TG_TUNE_DEFAULT_ONLY  // tools/tune_edge_bwd.sh: compile the default workload's kernel alone (seconds instead of minutes)
     if (heads == 2 && vec && out_channels == 11 && dtype == TECGAT_F32) rc = launch_bwd<11, float, true, 2>(a, plan, grid, st);
     else return TECGAT_ENOSUP;
 #else

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Runs on the GPU box: links every edge_bwd variant object under gpurun_scratch/variants/ (built here with
-# -DTG_TUNE_DEFAULT_ONLY -DTG_TUNE=<bits>, seconds each) against the in-tree objects and times the default workload with each
+# -DTG_TUNE_DEFAULT_ONLY plus whatever -D switch is being compared, seconds each) against the in-tree objects and times the default workload with each
 # (TECGAT_LIB).  ptxas schedules the two edge loops of edge_bwd differently after ANY change to the kernel (+-4 %).
 cd "${GRAFT_REPO_ROOT:-/root/repo}"; mkdir -p gpurun_out
 OBJS=$(ls tec_mollm_b200/build/*.o | grep -v "/edge_bwd.o")
