@@ -1,7 +1,13 @@
 #!/bin/bash
-# Runs on the GPU box: links every edge_bwd variant object under gpurun_scratch/variants/ (built here with
-# -DTG_TUNE_DEFAULT_ONLY plus whatever -D switch is being compared, seconds each) against the in-tree objects and times the default workload with each
-# (TECGAT_LIB).  ptxas schedules the two edge loops of edge_bwd differently after ANY change to the kernel (+-4 %).
+# A/B harness for edge_bwd source variants on the default workload (one B200).  Build the variant objects HERE (5 s each: only the
+# default workload's kernel is instantiated), e.g.
+#   mkdir -p gpurun_scratch/variants
+#   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -ffp-contract=off \
+#        -I tec_mollm_b200/csrc -I include -DTG_TUNE_DEFAULT_ONLY -D<SWITCH> -c tec_mollm_b200/csrc/edge_bwd.cu \
+#        -o gpurun_scratch/variants/edge_bwd_t<name>.o
+# then `gpurun -- bash tools/tune_edge_bwd.sh`: every object is linked against the in-tree objects on the box and timed twice
+# through bench.py (TECGAT_LIB selects the library).  ptxas compiles each kernel on its own, so the trimmed object's SASS is
+# identical to the full build's (checked).  Findings: profiles/r02_item_schedule.md.
 cd "${GRAFT_REPO_ROOT:-/root/repo}"; mkdir -p gpurun_out
 OBJS=$(ls tec_mollm_b200/build/*.o | grep -v "/edge_bwd.o")
 for v in gpurun_scratch/variants/edge_bwd_t*.o; do
