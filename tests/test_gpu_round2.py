@@ -103,9 +103,11 @@ def test_graph_replay_draws_fresh_dropout_masks(cuda_device):
     _check(outs[1][0], grads, y_ref, g_ref, TOL_F32, "graph replay 2")
 
 
-def test_graphed_callable_matches_eager(cuda_device):
-    """SpatialEncoder.graphed(): the opt-in CUDA-graph mode (forward and backward each one replay) equals the eager module."""
-    S, N, F, H, C = 96, 2911, 22, 2, 11
+@pytest.mark.parametrize("S,H", [(96, 2), (8, 4)])
+def test_graphed_callable_matches_eager(cuda_device, S, H):
+    """SpatialEncoder.graphed(): the opt-in CUDA-graph mode (forward and backward each one replay) equals the eager module
+    (H = 4: the head-pair path, two launches per phase, inside the captured graphs)."""
+    N, F, C = 2911, 22, 11
     ei = _cn150(cuda_device)
     x, gy, p = _rand_case(S, N, F, H, C, seed=5, dtype=torch.float32)
     enc = _encoder(F, H, C, p, cuda_device).eval()
