@@ -195,7 +195,8 @@ __device__ __forceinline__ ItemRange cta_items_scheduled(const ItemSchedule &s, 
 inline void fill_schedule(ItemSchedule &s, const tecgat_plan_t *plan, bool bwd, int64_t snapshots, int grid) {
     s.use = 0;
     s.pad = 0;
-    if (grid > kMaxSchedGrid) return;
+    const char *knob = tg_env("TECGAT_SCHEDULE");  // A/B knob: "closed" = the closed-form equal-count split computed in the kernel
+    if (grid > kMaxSchedGrid || (knob && knob[0] == 'c' && knob[1] == 'l')) return;
     const int64_t *b = tg_item_bounds(plan, bwd, snapshots, grid, nullptr);
     for (int i = 0; i <= grid; ++i) s.bounds[i] = b[i];
     s.use = 1;

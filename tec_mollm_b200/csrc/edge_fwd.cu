@@ -133,7 +133,9 @@ __device__ __forceinline__ void fwd_lane(const int Ts /* slab row stride */, con
 // HT > 0: compile-time number of heads (address arithmetic folds); 0: runtime
 // GATHER: the launch contains tiles that are not staged (false drops the gather-from-global code: every item is staged).
 // TT > 0: compile-time tile size (nodes) -- the default 15 consumer warps x 32 / heads: the slab strides become immediates
-template <int C, typename ST, bool VEC, int HT, bool GATHER, bool DROP, int TT = 0>
+// WIDE: the output rows are also stored into a wider row-major tensor (a.y2, head pairs of a layer with more than two heads);
+// a separate instantiation so that the default kernels carry none of it
+template <int C, typename ST, bool VEC, int HT, bool GATHER, bool DROP, int TT = 0, bool WIDE = false>
 __global__ void __launch_bounds__(512, 1) edge_fwd_kernel(const __grid_constant__ EdgeFwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem);
@@ -262,7 +264,7 @@ __global__ void __launch_bounds__(512, 1) edge_fwd_kernel(const __grid_constant_
             } else {
                 for (int i = lane; i < nv * HC; i += 32) y_g[i] = ybuf[i];
             }
-            if (a.y2) {  // the same rows into the caller's wider tensor (one HC-float run per row)
+            if constexpr (WIDE) {  // the same rows into the caller's wider tensor (one HC-float run per row)
                 float *y_w = a.y2 + ((int64_t)snap * N + n0 + warp * npw) * a.ld2;
                 if (VEC) {
                     const int hw = HC / 2;
@@ -292,7 +294,9 @@ __global__ void __launch_bounds__(512, 1) edge_fwd_kernel(const __grid_constant_
             fwd_lane<C, ST, VEC, false, DROP>(Ts, a, attp, attm, bias_h, xr_chunk, xl_snap + (int64_t)(n0 + node_l) * HC, xl_snap, HC, par, nullptr,
                                         a.col + k0, deg, kmax_w, (uint32_t)k0, key, out, stat);
             if (active) cv_store<C, VEC>(a.y + row * HC + hh * C, out, par);
-            if (active && a.y2) cv_store<C, VEC>(a.y2 + row * a.ld2 + hh * C, out, par);
+            if constexpr (WIDE) {
+                if (active) cv_store<C, VEC>(a.y2 + row * a.ld2 + hh * C, out, par);
+            }
         }
         if (active) a.stat[row * H + hh] = stat;
         if (++tile == a.num_tiles) { tile = 0; ++snap; }
@@ -418,6 +422,15 @@ static int launch_fwd(EdgeFwdArgs a, const tecgat_plan_t *plan, cudaStream_t st)
     };
     int rc;
     constexpr int kTT = HT > 0 ? 15 * (32 / pad_heads(HT > 0 ? HT : 1)) : 0;  // the default tile of the fixed-head kernels
+    if (a.y2) {  // wide output: compiled for the fixed-head shapes only (dropout off = threshold 0 in the hashing kernels)
+        rc = TECGAT_ENOSUP;
+        if constexpr (HT > 0) {
+            if (all_staged && T == kTT) rc = go(edge_fwd_kernel<C, ST, VEC, HT, false, true, kTT, true>);
+            else if (all_staged) rc = go(edge_fwd_kernel<C, ST, VEC, HT, false, true, 0, true>);
+            else rc = go(edge_fwd_kernel<C, ST, VEC, HT, true, true, 0, true>);
+        }
+        if (rc == TECGAT_ENOSUP) tecgat_set_error("edge_fwd: the wide output exists only for heads = 2, out_channels 5 or 11");
+    } else
     if (HT > 0 && all_staged && T == kTT && a.drop_thr == 0) rc = go(edge_fwd_kernel<C, ST, VEC, HT, HT == 0, HT == 0, kTT>);
     else if (HT > 0 && all_staged && T == kTT) rc = go(edge_fwd_kernel<C, ST, VEC, HT, HT == 0, true, kTT>);
     else if (HT > 0 && all_staged && a.drop_thr == 0) rc = go(edge_fwd_kernel<C, ST, VEC, HT, HT == 0, HT == 0>);  // inference: no hash either

@@ -468,9 +468,8 @@ class GATv2Conv(nn.Module):
     # it gathers rows from L2 instead), and the two-head shapes are the ones compiled with fixed tile sizes.
     def _split_head_pairs(self) -> bool:
         knob = os.environ.get("TECGAT_HEAD_SPLIT")  # tests: "0" keeps the one-launch kernels for any head count
-        if knob is not None:
-            return knob != "0" and self.heads > 2 and self.heads % 2 == 0
-        return self.heads > 2 and self.heads % 2 == 0 and self.out_channels in (5, 11)
+        ok = self.heads > 2 and self.heads % 2 == 0 and self.out_channels in (5, 11)  # the compiled two-head shapes
+        return ok and knob != "0"
 
     def _forward_head_pairs(self, x, edge_index, snapshots, num_nodes, p, mode, dtype):
         plan = self.plan_for(edge_index, num_nodes, (tile_nodes_for(2), tile_nodes_for(2, backward=True, out_channels=self.out_channels)))
