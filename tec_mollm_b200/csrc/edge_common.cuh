@@ -277,10 +277,12 @@ __device__ __forceinline__ void acc_step(CV<C> &B, const CV<C> &s, float de) {
     const float2 de2 = splat(de);
 #pragma unroll
     for (int i = 0; i < CV<C>::NP; ++i) {
-        const float2 step = make_float2(s.p[i].x > 0.f ? 1.f : 0.f, s.p[i].y > 0.f ? 1.f : 0.f);
+        // [s > 0] as saturate(s * 1e38): FMUL.SAT on the FMA pipe instead of FSET on the (busier per instruction) ALU pipe --
+        // 0.9 % of edge_bwd; exact for |s| >= 1e-38, i.e. everywhere but inside the kink
+        const float2 step = make_float2(__saturatef(s.p[i].x * 1.0e38f), __saturatef(s.p[i].y * 1.0e38f));
         B.p[i] = __ffma2_rn(de2, step, B.p[i]);
     }
-    if (CV<C>::ODD) B.s = fmaf(de, s.s > 0.f ? 1.f : 0.f, B.s);
+    if (CV<C>::ODD) B.s = fmaf(de, s.s > 0.f ? 1.f : 0.f, B.s);  // (measured: the compare is the faster form for the odd channel)
 }
 template <int C>
 __device__ __forceinline__ void cv_axpy(CV<C> &y, float a, const CV<C> &x) {
